@@ -1,0 +1,274 @@
+// Shared device/host helpers for libharmonic_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/harmonic_b200.h"
+
+namespace hb {
+
+// ------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define HB_CUDA(call)                                                         \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) return hb::cuda_fail(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define HB_REQUIRE(cond, msg)   \
+  do {                          \
+    if (!(cond)) {              \
+      hb::set_error(msg);       \
+      return HB_ERR_INVALID;    \
+    }                           \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// per-chain streaming state and launch partials
+// ------------------------------------------------------------------------------------------
+// state[c] = {m, s, n, n_nan}: ln sum_i exp(lnarg_i) = m + ln s over the finite lnargs of chain c
+// (the shift-free form of Evidence.running_sum, harmonic/evidence.py:321-334), n = all samples
+// (NaNs included, :337-338), n_nan (:342-345).
+struct ChainState {
+  double m, s, n, nnan;
+};
+// one record per (chain, flusher) pair written by the accumulate kernels; merged in a fixed
+// order by merge_kernel so the result does not depend on scheduling.
+struct ChainRec {
+  double m, s, nnan, valid;
+};
+enum { G_SUM = 0, G_CNT, G_ARGMAX, G_ARGMIN, G_PROBMAX, G_PROBMIN, G_PREDMAX, G_PREDMIN, G_N };
+
+struct FoldParams {
+  const long long* start;  // device, nch+1 local row offsets of the chains of this launch
+  int nch;
+  long long nrows;
+  long long rows_per_flusher;  // contiguous rows owned by one flusher (multiple of its tile)
+  ChainRec* recs;              // [nch + nflushers], zeroed before the launch
+  double* gpart;               // [nflushers][G_N]
+};
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float nanmaxf(float a, float b) { return fmaxf(a, b); }  // fmaxf drops NaN
+__device__ __forceinline__ float nanminf(float a, float b) { return fminf(a, b); }
+
+// Fold: every thread of a "flusher" group (NT threads synchronised on named barrier BAR) feeds
+// the rows it owns; rows of one flusher are a contiguous range, walked tile by tile in order.
+// Implements lnarg = lnpred - lnpost, +-inf -> NaN (harmonic/evidence.py:278-283), NaN counting
+// (:342-345), the per-chain sums (:321-334, as a max-rescaled online logsumexp) and the six
+// nan-aware extrema + mean-shift sums (:307-319,347-352).
+template <int NT, int BAR>
+struct Fold {
+  // uniform across the group
+  const FoldParams& p;
+  int flusher;
+  int cur_chain;
+  long long cur_end;  // local row where cur_chain ends
+  int tid;            // 0..NT-1 within the group
+  double* scratch;    // shared, >= 3*(NT/32) doubles, private to the group
+  // per thread
+  float m, s;
+  int nnan;
+  float gsum;
+  int gcnt;
+  float amax, amin, pmax, pmin, qmax, qmin;
+
+  __device__ Fold(const FoldParams& p_, int flusher_, int tid_, double* scratch_, long long row_lo)
+      : p(p_), flusher(flusher_), tid(tid_), scratch(scratch_) {
+    m = -CUDART_INF_F;
+    s = 0.f;
+    nnan = 0;
+    gsum = 0.f;
+    gcnt = 0;
+    amax = pmax = qmax = -CUDART_INF_F;
+    amin = pmin = qmin = CUDART_INF_F;
+    // chain containing row_lo: largest c with start[c] <= row_lo (then skip empty chains)
+    int lo = 0, hi = p.nch;  // invariant: start[lo] <= row_lo
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (p.start[mid] <= row_lo) lo = mid; else hi = mid;
+    }
+    cur_chain = lo;
+    cur_end = (cur_chain < p.nch) ? p.start[cur_chain + 1] : (long long)0x7fffffffffffffffLL;
+    while (cur_chain < p.nch && cur_end <= row_lo) {
+      ++cur_chain;
+      cur_end = (cur_chain < p.nch) ? p.start[cur_chain + 1] : (long long)0x7fffffffffffffffLL;
+    }
+  }
+
+  __device__ __forceinline__ void sample(float lnpred, float lnpost) {
+    float a = lnpred - lnpost;
+    qmax = nanmaxf(qmax, lnpred);
+    qmin = nanminf(qmin, lnpred);
+    pmax = nanmaxf(pmax, lnpost);
+    pmin = nanminf(pmin, lnpost);
+    if (isnan(a) || isinf(a)) {
+      ++nnan;
+    } else {
+      if (a > m) {
+        s = s * __expf(m - a) + 1.f;
+        m = a;
+      } else {
+        s += __expf(a - m);
+      }
+      gsum += a;
+      ++gcnt;
+      amax = fmaxf(amax, a);
+      amin = fminf(amin, a);
+    }
+  }
+
+  // group-wide reduction of (m, s, nnan); result valid in tid 0. All NT threads must call.
+  __device__ void flush() {
+    constexpr int NW = NT / 32;
+    float mw = m;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    double sw = (s > 0.f) ? (double)s * exp((double)m - (double)mw) : 0.0;
+    int nw = nnan;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      sw += __shfl_xor_sync(0xffffffffu, sw, o);
+      nw += __shfl_xor_sync(0xffffffffu, nw, o);
+    }
+    if ((tid & 31) == 0) {
+      scratch[(tid >> 5) * 3 + 0] = (double)mw;
+      scratch[(tid >> 5) * 3 + 1] = sw;
+      scratch[(tid >> 5) * 3 + 2] = (double)nw;
+    }
+    named_bar_sync(BAR, NT);
+    if (tid == 0) {
+      double M = -CUDART_INF, S = 0.0, NN = 0.0;
+      for (int w = 0; w < NW; ++w) M = fmax(M, scratch[w * 3]);
+      for (int w = 0; w < NW; ++w) {
+        double sv = scratch[w * 3 + 1];
+        if (sv > 0.0) S += sv * exp(scratch[w * 3] - M);
+        NN += scratch[w * 3 + 2];
+      }
+      ChainRec r;
+      r.m = M;
+      r.s = S;
+      r.nnan = NN;
+      r.valid = 1.0;
+      p.recs[cur_chain + flusher] = r;
+    }
+    named_bar_sync(BAR, NT);
+    m = -CUDART_INF_F;
+    s = 0.f;
+    nnan = 0;
+  }
+
+  // Feed one tile [t0, t1) of the flusher's rows. Thread owns rows t0 + tid*R + q, q < R.
+  template <int R>
+  __device__ __forceinline__ void tile(long long t0, long long t1, const float (&lnpred)[R],
+                                       const float (&lnpost)[R]) {
+    long long seg_begin = t0;
+    const long long r0 = t0 + (long long)tid * R;
+    while (true) {
+      const long long seg_end = (t1 < cur_end) ? t1 : cur_end;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const long long r = r0 + q;
+        if (r >= seg_begin && r < seg_end) sample(lnpred[q], lnpost[q]);
+      }
+      if (cur_chain < p.nch && cur_end <= t1) {
+        flush();
+        seg_begin = cur_end;
+        do {
+          ++cur_chain;
+          cur_end = (cur_chain < p.nch) ? p.start[cur_chain + 1] : (long long)0x7fffffffffffffffLL;
+        } while (cur_chain < p.nch && cur_end <= seg_begin);
+        if (seg_begin >= t1 || cur_chain >= p.nch) break;
+      } else {
+        break;
+      }
+    }
+  }
+
+  // End of the flusher's range: flush the open chain and the per-call scalars.
+  __device__ void finish(bool had_rows) {
+    if (had_rows && cur_chain < p.nch) flush();
+    constexpr int NW = NT / 32;
+    double gs = gsum, gc = gcnt;
+    float v[6] = {amax, amin, pmax, pmin, qmax, qmin};
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      gs += __shfl_xor_sync(0xffffffffu, gs, o);
+      gc += __shfl_xor_sync(0xffffffffu, gc, o);
+#pragma unroll
+      for (int k = 0; k < 6; k += 2) {
+        v[k] = fmaxf(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+        v[k + 1] = fminf(v[k + 1], __shfl_xor_sync(0xffffffffu, v[k + 1], o));
+      }
+    }
+    // scratch holds 3*NW doubles; reuse it in three rounds of (sum,cnt | extrema)
+    named_bar_sync(BAR, NT);
+    double out[G_N];
+    for (int k = 0; k < G_N; ++k) {
+      double mine = (k == 0) ? gs : (k == 1) ? gc : (double)v[k - 2];
+      if ((tid & 31) == 0) scratch[tid >> 5] = mine;
+      named_bar_sync(BAR, NT);
+      if (tid == 0) {
+        double acc = scratch[0];
+        for (int w = 1; w < NW; ++w) {
+          double o = scratch[w];
+          if (k < 2) acc += o;
+          else if (k & 1) acc = fmin(acc, o);  // odd k = minima (ARGMIN=3, PROBMIN=5, PREDMIN=7)
+          else acc = fmax(acc, o);
+        }
+        out[k] = acc;
+      }
+      named_bar_sync(BAR, NT);
+    }
+    if (tid == 0) {
+      for (int k = 0; k < G_N; ++k) p.gpart[(long long)flusher * G_N + k] = out[k];
+    }
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p, long long i) {
+  return (float)p[i];
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------
+// host-side handles
+// ------------------------------------------------------------------------------------------
+struct Accum {
+  int device = 0;
+  long long nchains = 0;
+  ChainState* state = nullptr;  // device [nchains]
+  double* globals = nullptr;    // device [G_N] per-call scalars
+  long long* start_dev = nullptr;  // device [nchains+1] scratch for the local offsets
+  ChainRec* recs = nullptr;        // device scratch
+  size_t recs_cap = 0;
+  double* gpart = nullptr;  // device scratch
+  size_t gpart_cap = 0;
+  // staging for HOST inputs (pinned + device, double-buffered)
+  void* pin[2] = {nullptr, nullptr};
+  void* dev[2] = {nullptr, nullptr};
+  size_t stage_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  // finalize outputs
+  double* fin = nullptr;  // device: hb_result + 4*nchains doubles
+};
+
+}  // namespace hb

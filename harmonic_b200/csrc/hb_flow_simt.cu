@@ -1,0 +1,628 @@
+// CUDA-core FP32 flow kernels (one sample per thread): the general-shape path for RealNVP and the
+// RQSpline path, both fused with the per-chain fold.  Also the on-device cross-check for the
+// tcgen05 RealNVP kernel.
+//
+// Reference arithmetic replaced: harmonic/flows.py:41-116,159-180 (RealNVP via tfp-jax) and
+// :234-288,335-438 (RQSpline via distrax); harmonic/model.py:222-235 (standardisation);
+// fused with harmonic/evidence.py:278-352.  Per-sample restatement: SURVEY.md Appendix A.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "hb_internal.h"
+
+namespace hb {
+
+constexpr int FT = 128;  // threads per CTA = rows per tile
+constexpr int MAX_LAYERS = 64;
+
+struct SimtLayer {
+  int w0, b0, w2, b2;  // offsets (floats) into the packed buffer
+  int n2, n2pad;       // outputs of the second dense (u or 2u) and padded width
+  int scaled;
+};
+struct RealNVPSimtParams {
+  const float* pack;
+  const float* pre;  // pre_offset[D], pre_amp[D] or nullptr
+  int D, d, u, nlayers;
+  float T, sum_log_amp;
+  SimtLayer layers[MAX_LAYERS];
+};
+
+__device__ __forceinline__ float softplus_acc(float a) {
+  return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a)));
+}
+
+// out[j] = act(b[j] + sum_i in[phys(i)] * W[i][j]); activations live in shared memory as
+// [feature][thread] columns; weights are read through the read-only path (warp-uniform
+// addresses -> one broadcast transaction per float4).
+template <int ACT, class Phys, class Use>
+__device__ __forceinline__ void dense_cols(const float* in_s, Phys phys, Use use, int n_in,
+                                           const float* __restrict__ W, int ldw,
+                                           const float* __restrict__ b, int n_out, float* out_s,
+                                           int tid) {
+  for (int j0 = 0; j0 < n_out; j0 += 8) {
+    float acc[8];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + j0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + j0 + 4));
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+    for (int i = 0; i < n_in; ++i) {
+      if (!use(i)) continue;
+      const float a = in_s[phys(i) * FT + tid];
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)i * ldw + j0));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)i * ldw + j0 + 4));
+      acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]);
+      acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
+      acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
+      acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (j0 + q < n_out) {
+        float v = acc[q];
+        if (ACT == 1) v = tanhf(v);
+        if (ACT == 2) v = (v >= 0.f) ? v : 0.01f * v;
+        out_s[(j0 + q) * FT + tid] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// RealNVP, any ndim >= 2.  Shared memory: y[D][128] | h[128][128] | o[n2max][128].
+// ------------------------------------------------------------------------------------------
+template <typename XT, typename LT, bool FOLD>
+__global__ void __launch_bounds__(FT)
+realnvp_simt_kernel(RealNVPSimtParams P, const XT* __restrict__ x, long long ld,
+                    const LT* __restrict__ lnpost, float* __restrict__ lnpred_out, FoldParams fp,
+                    long long nrows, long long rows_per_cta) {
+  extern __shared__ float smem[];
+  __shared__ double scratch[3 * (FT / 32)];
+  const int tid = threadIdx.x;
+  const int D = P.D, d = P.d, u = P.u;
+  float* ys = smem;
+  float* hs = ys + (size_t)D * FT;
+  float* os = hs + (size_t)128 * FT;
+  const long long row_lo = (long long)blockIdx.x * rows_per_cta;
+  long long row_hi = row_lo + rows_per_cta;
+  if (row_hi > nrows) row_hi = nrows;
+  const bool had_rows = row_lo < nrows;
+  Fold<FT, 0> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
+  const float invT = 1.f / P.T;
+  const float base_const = -(float)D * logf(P.T) - 0.5f * (float)D * 1.8378770664093453f;
+
+  for (long long t0 = row_lo; t0 < row_hi; t0 += FT) {
+    const long long r = t0 + tid;
+    const bool live = r < row_hi;
+    const long long rr = live ? r : t0;  // dead threads recompute row t0 (never stored/folded)
+    for (int i = 0; i < D; ++i) {
+      float v = (float)x[rr * ld + i];
+      if (P.pre) v = (v - P.pre[i]) / P.pre[D + i];
+      ys[i * FT + tid] = v;
+    }
+    float ldj = 0.f;
+    for (int l = 0; l < P.nlayers; ++l) {
+      const SimtLayer L = P.layers[l];
+      const int rot = l % D;  // logical y[i] lives in physical row (i + l) mod D
+      auto phys = [&](int i) { int k = i + rot; return k >= D ? k - D : k; };
+      auto all = [](int) { return true; };
+      dense_cols<2>(ys, phys, all, d, P.pack + L.w0, 128, P.pack + L.b0, 128, hs, tid);
+      dense_cols<0>(hs, [](int i) { return i; }, all, 128, P.pack + L.w2, L.n2pad, P.pack + L.b2,
+                    L.n2, os, tid);
+      for (int k = 0; k < u; ++k) {
+        const int pk = phys(d + k);
+        float y1 = ys[pk * FT + tid] - os[k * FT + tid];
+        if (L.scaled) {
+          float sc = softplus_acc(os[(u + k) * FT + tid]);
+          sc = fminf(fmaxf(sc, 1e-3f), 1e3f);
+          y1 = y1 / sc;
+          ldj -= logf(sc);
+        }
+        ys[pk * FT + tid] = y1;
+      }
+    }
+    float ss = 0.f;
+    for (int i = 0; i < D; ++i) {
+      const float z = ys[i * FT + tid] * invT;
+      ss = fmaf(z, z, ss);
+    }
+    const float lnphi = -0.5f * ss + base_const + ldj - P.sum_log_amp;
+    if (live && lnpred_out) lnpred_out[r] = lnphi;
+    if (FOLD) {
+      float a[1] = {lnphi};
+      float b[1] = {live ? (float)lnpost[r] : 0.f};
+      const long long t1 = (t0 + FT < row_hi) ? t0 + FT : row_hi;
+      fold.tile<1>(t0, t1, a, b);
+    }
+  }
+  if (FOLD) fold.finish(had_rows);
+}
+
+// ------------------------------------------------------------------------------------------
+// RQSpline, any ndim / hidden sizes.  Packed weights per flow layer i:
+//   MLP dense m = 0..nmlp-2 (each followed by tanh): W[in][outpad], b[outpad]
+//   per transformed feature j: fused (last MLP dense) x (output dense rows of j):
+//       M_j[in_last][npar_pad], c_j[npar_pad]          (no activation in between, flows.py:434-438)
+//   scales[D], shifts[D]
+// ------------------------------------------------------------------------------------------
+constexpr int RQ_MAX_MLP = HB_MAX_HIDDEN + 1;
+struct RQLayer {
+  int w[RQ_MAX_MLP], b[RQ_MAX_MLP];  // hidden denses (with tanh)
+  int fused;                         // offset of the first feature block; blocks are contiguous
+  int scales, shifts;
+};
+struct RQParams {
+  const float* pack;
+  const float* pre;
+  int D, K, npar, npar_pad, nlayers;
+  int nact;                  // number of tanh denses = nmlp - 1
+  int width[RQ_MAX_MLP + 1];  // width[0] = D (input), width[m+1] = out of dense m
+  int wpad[RQ_MAX_MLP + 1];
+  int in_last;                // input width of the fused dense
+  int maxw;                   // max activation width
+  float lo, hi, T, sum_log_amp;
+  const RQLayer* layers;  // device
+};
+
+// distrax.RationalQuadraticSpline forward + log-det for one scalar; params in a smem column.
+__device__ __forceinline__ void rqs_forward(float x, const float* ps, int tid, int K, float lo,
+                                            float hi, float& yout, float& ldout) {
+  const float mbs = 1e-4f, mks = 1e-4f;
+  const float off = logf(expf(1.f - mks) - 1.f);
+  const float R = hi - lo;
+  const float span = R - (float)K * mbs;
+  float mw = -CUDART_INF_F, mh = -CUDART_INF_F;
+  for (int k = 0; k < K; ++k) {
+    mw = fmaxf(mw, ps[k * FT + tid]);
+    mh = fmaxf(mh, ps[(K + k) * FT + tid]);
+  }
+  float sw = 0.f, shh = 0.f;
+  for (int k = 0; k < K; ++k) {
+    sw += expf(ps[k * FT + tid] - mw);
+    shh += expf(ps[(K + k) * FT + tid] - mh);
+  }
+  if (x <= lo) {
+    const float s0 = softplus_acc(ps[(2 * K) * FT + tid] + off) + mks;
+    yout = (x - lo) * s0 + lo;
+    ldout = logf(s0);
+    return;
+  }
+  if (x >= hi) {
+    const float sK = softplus_acc(ps[(3 * K) * FT + tid] + off) + mks;
+    yout = (x - hi) * sK + hi;
+    ldout = logf(sK);
+    return;
+  }
+  // knots: xk[0]=lo, xk[k]=lo+cumsum(w)[k-1], xk[K]=hi (same for yk)
+  float xl = lo, yl = lo, cw = 0.f, chh = 0.f;
+  float bxl = lo, bxr = lo, byl = lo, byr = lo;
+  int kb = -1;
+  for (int k = 0; k < K; ++k) {
+    const float w = expf(ps[k * FT + tid] - mw) / sw * span + mbs;
+    const float h = expf(ps[(K + k) * FT + tid] - mh) / shh * span + mbs;
+    cw += w;
+    chh += h;
+    const float xr = (k == K - 1) ? hi : lo + cw;
+    const float yr = (k == K - 1) ? hi : lo + chh;
+    if (k == 0) { bxl = xl; bxr = xr; byl = yl; byr = yr; }  // default bin 0 (e.g. NaN input)
+    if (kb < 0 && x >= xl && x < xr) {
+      kb = k; bxl = xl; bxr = xr; byl = yl; byr = yr;
+    }
+    xl = xr;
+    yl = yr;
+  }
+  if (kb < 0) kb = 0;
+  const float sl = softplus_acc(ps[(2 * K + kb) * FT + tid] + off) + mks;
+  const float sr = softplus_acc(ps[(2 * K + kb + 1) * FT + tid] + off) + mks;
+  const float bw = bxr - bxl, bh = byr - byl;
+  const float delta = bh / bw;
+  float z = (x - bxl) / bw;
+  z = fminf(fmaxf(z, 0.f), 1.f);
+  if (isnan(x)) z = x;  // jnp.clip propagates NaN; fminf/fmaxf would drop it
+  const float sq_z = z * z;
+  const float z1mz = z - sq_z;
+  const float omz = 1.f - z;
+  const float sq_1mz = omz * omz;
+  const float slopes_term = sr + sl - 2.f * delta;
+  const float numerator = bh * (delta * sq_z + sl * z1mz);
+  const float denominator = delta + slopes_term * z1mz;
+  yout = byl + numerator / denominator;
+  ldout = 2.f * logf(delta) + logf(sr * sq_z + 2.f * delta * z1mz + sl * sq_1mz) -
+          2.f * logf(denominator);
+}
+
+template <typename XT, typename LT, bool FOLD>
+__global__ void __launch_bounds__(FT)
+rqspline_simt_kernel(RQParams P, const XT* __restrict__ x, long long ld,
+                     const LT* __restrict__ lnpost, float* __restrict__ lnpred_out, FoldParams fp,
+                     long long nrows, long long rows_per_cta) {
+  extern __shared__ float smem[];
+  __shared__ double scratch[3 * (FT / 32)];
+  const int tid = threadIdx.x;
+  const int D = P.D, K = P.K;
+  float* ys = smem;                              // [D][FT]
+  float* bufA = ys + (size_t)D * FT;             // [maxw][FT]
+  float* bufB = bufA + (size_t)P.maxw * FT;      // [maxw][FT]
+  float* ps = bufB + (size_t)P.maxw * FT;        // [npar_pad][FT]
+  const long long row_lo = (long long)blockIdx.x * rows_per_cta;
+  long long row_hi = row_lo + rows_per_cta;
+  if (row_hi > nrows) row_hi = nrows;
+  const bool had_rows = row_lo < nrows;
+  Fold<FT, 0> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
+  const float base_const = -0.5f * (float)D * 1.8378770664093453f - 0.5f * (float)D * logf(P.T);
+  auto ident = [](int i) { return i; };
+  auto all = [](int) { return true; };
+
+  for (long long t0 = row_lo; t0 < row_hi; t0 += FT) {
+    const long long r = t0 + tid;
+    const bool live = r < row_hi;
+    const long long rr = live ? r : t0;
+    for (int i = 0; i < D; ++i) {
+      float v = (float)x[rr * ld + i];
+      if (P.pre) v = (v - P.pre[i]) / P.pre[D + i];
+      ys[i * FT + tid] = v;
+    }
+    float ldet = 0.f;
+    for (int i = P.nlayers - 1; i >= 0; --i) {  // Inverse(Chain).inverse: last layer first
+      const RQLayer L = P.layers[i];
+      const int par = i & 1;  // mask = (j%2==1) for even i, negated for odd i; True = pass-through
+      auto visible = [&](int j) { return ((j & 1) == 1) != (par == 1); };
+      // conditioner MLP on where(mask, y, 0)
+      const float* cur = ys;
+      float* nxt = bufA;
+      for (int m = 0; m < P.nact; ++m) {
+        if (m == 0)
+          dense_cols<1>(cur, ident, visible, P.width[0], P.pack + L.w[0], P.wpad[1], P.pack + L.b[0],
+                        P.width[1], nxt, tid);
+        else
+          dense_cols<1>(cur, ident, all, P.width[m], P.pack + L.w[m], P.wpad[m + 1], P.pack + L.b[m],
+                        P.width[m + 1], nxt, tid);
+        cur = nxt;
+        nxt = (nxt == bufA) ? bufB : bufA;
+      }
+      // spline on every non-visible feature, params from the fused last dense
+      int blk = 0;
+      const size_t blk_floats = (size_t)P.in_last * P.npar_pad + P.npar_pad;
+      for (int j = 0; j < D; ++j) {
+        if (visible(j)) continue;
+        const float* Mj = P.pack + L.fused + blk * blk_floats;
+        const float* cj = Mj + (size_t)P.in_last * P.npar_pad;
+        if (P.nact == 0)
+          dense_cols<0>(ys, ident, visible, P.in_last, Mj, P.npar_pad, cj, P.npar, ps, tid);
+        else
+          dense_cols<0>(cur, ident, all, P.in_last, Mj, P.npar_pad, cj, P.npar, ps, tid);
+        float yo, lo_;
+        rqs_forward(ys[j * FT + tid], ps, tid, K, P.lo, P.hi, yo, lo_);
+        ys[j * FT + tid] = yo;
+        ldet += lo_;
+        ++blk;
+      }
+      // scalar affine, all dims
+      for (int j = 0; j < D; ++j) {
+        const float sc = __ldg(P.pack + L.scales + j), sh = __ldg(P.pack + L.shifts + j);
+        ys[j * FT + tid] = fmaf(ys[j * FT + tid], sc, sh);
+        ldet += logf(fabsf(sc));
+      }
+    }
+    float ss = 0.f;
+    for (int j = 0; j < D; ++j) {
+      const float v = ys[j * FT + tid];
+      ss = fmaf(v, v, ss);
+    }
+    const float lnphi = -0.5f * ss / P.T + base_const + ldet - P.sum_log_amp;
+    if (live && lnpred_out) lnpred_out[r] = lnphi;
+    if (FOLD) {
+      float a[1] = {lnphi};
+      float b[1] = {live ? (float)lnpost[r] : 0.f};
+      const long long t1 = (t0 + FT < row_hi) ? t0 + FT : row_hi;
+      fold.tile<1>(t0, t1, a, b);
+    }
+  }
+  if (FOLD) fold.finish(had_rows);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int pad8(int n) { return (n + 7) & ~7; }
+
+// Packed SIMT weights are built lazily and cached on the Flow (rq_pack is reused for RealNVP).
+static int realnvp_simt_prepare(Flow* f, RealNVPSimtParams* P) {
+  if (f->simt_params) {
+    *P = *static_cast<RealNVPSimtParams*>(f->simt_params);
+    return HB_OK;
+  }
+  const int D = f->desc.ndim, d = f->d, u = f->u;
+  const int nl = f->nlayers;
+  if (nl > MAX_LAYERS) {
+    set_error("RealNVP: more than 64 coupling layers are not supported");
+    return HB_ERR_UNSUPPORTED;
+  }
+  std::vector<float> pack;
+  auto align4 = [&]() { while (pack.size() % 4) pack.push_back(0.f); };
+  const float* w = f->host_weights.data();
+  for (int l = 0; l < nl; ++l) {
+    const bool scaled = l < f->desc.n_scaled;
+    const float* base = w + f->layer_off[l];
+    const float* W0 = base;
+    const float* b0 = W0 + (size_t)d * 128;
+    const float* Wt = b0 + 128;
+    const float* bt = Wt + (size_t)128 * u;
+    const float* Ws = bt + u;
+    const float* bs = Ws + (size_t)128 * u;
+    SimtLayer& L = P->layers[l];
+    L.scaled = scaled;
+    L.n2 = scaled ? 2 * u : u;
+    L.n2pad = pad8(L.n2);
+    align4();
+    L.w0 = (int)pack.size();
+    pack.insert(pack.end(), W0, W0 + (size_t)d * 128);
+    L.b0 = (int)pack.size();
+    pack.insert(pack.end(), b0, b0 + 128);
+    L.w2 = (int)pack.size();
+    for (int j = 0; j < 128; ++j)
+      for (int k = 0; k < L.n2pad; ++k) {
+        float v = 0.f;
+        if (k < u) v = Wt[(size_t)j * u + k];
+        else if (scaled && k < 2 * u) v = Ws[(size_t)j * u + (k - u)];
+        pack.push_back(v);
+      }
+    L.b2 = (int)pack.size();
+    for (int k = 0; k < L.n2pad; ++k) {
+      float v = 0.f;
+      if (k < u) v = bt[k];
+      else if (scaled && k < 2 * u) v = bs[k - u];
+      pack.push_back(v);
+    }
+  }
+  {
+    HB_CUDA(cudaMalloc(&f->rq_pack, pack.size() * sizeof(float)));
+    HB_CUDA(cudaMemcpy(f->rq_pack, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
+    f->rq_pack_floats = pack.size();
+  }
+  P->pack = f->rq_pack;
+  P->pre = f->desc.standardize ? f->dev_weights : nullptr;
+  P->D = D;
+  P->d = d;
+  P->u = u;
+  P->nlayers = nl;
+  P->sum_log_amp = f->sum_log_amp;
+  f->simt_params = new RealNVPSimtParams(*P);
+  return HB_OK;
+}
+
+void realnvp_simt_release(Flow* f) {
+  delete static_cast<RealNVPSimtParams*>(f->simt_params);
+  f->simt_params = nullptr;
+}
+
+#define HB_DISPATCH_XL(KERNEL, FOLDFLAG, ...)                                                    \
+  do {                                                                                           \
+    if (x_dtype == HB_F32 && lp_dtype == HB_F32)                                                 \
+      KERNEL<float, float, FOLDFLAG><<<grid, FT, smem, st>>>(P, (const float*)x, ld,             \
+                                                             (const float*)lnpost, __VA_ARGS__); \
+    else if (x_dtype == HB_F32)                                                                  \
+      KERNEL<float, double, FOLDFLAG><<<grid, FT, smem, st>>>(P, (const float*)x, ld,            \
+                                                              (const double*)lnpost, __VA_ARGS__); \
+    else if (lp_dtype == HB_F32)                                                                 \
+      KERNEL<double, float, FOLDFLAG><<<grid, FT, smem, st>>>(P, (const double*)x, ld,           \
+                                                              (const float*)lnpost, __VA_ARGS__); \
+    else                                                                                         \
+      KERNEL<double, double, FOLDFLAG><<<grid, FT, smem, st>>>(P, (const double*)x, ld,          \
+                                                               (const double*)lnpost, __VA_ARGS__); \
+  } while (0)
+
+#define HB_SET_SMEM(KERNEL, FOLDFLAG)                                                              \
+  do {                                                                                             \
+    cudaFuncSetAttribute(KERNEL<float, float, FOLDFLAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    cudaFuncSetAttribute(KERNEL<float, double, FOLDFLAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    cudaFuncSetAttribute(KERNEL<double, float, FOLDFLAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    cudaFuncSetAttribute(KERNEL<double, double, FOLDFLAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  } while (0)
+
+static void plan_grid(int device, long long n, size_t smem, long long* nfl, long long* rpc) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  int per_sm = (int)((227 * 1024) / (smem + 2048));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  long long f = (long long)sms * per_sm;
+  long long r = (n + f - 1) / f;
+  r = ((r + FT - 1) / FT) * FT;
+  *nfl = (n + r - 1) / r;
+  *rpc = r;
+}
+
+int realnvp_simt_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                     const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                     const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                     long long b, cudaStream_t st) {
+  if (n <= 0) return HB_OK;
+  RealNVPSimtParams P;
+  int rc = realnvp_simt_prepare(f, &P);
+  if (rc) return rc;
+  P.T = T;
+  const int D = P.D;
+  int n2max = 2 * P.u;
+  const size_t smem = ((size_t)D + 128 + n2max) * FT * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_error("RealNVP SIMT path: ndim too large for shared memory");
+    return HB_ERR_UNSUPPORTED;
+  }
+  long long nfl, rpc;
+  plan_grid(f->device, n, smem, &nfl, &rpc);
+  FoldParams fp{};
+  if (acc) {
+    rc = prepare_fold(acc, start, chain_lo, chain_hi, a, b, nfl, rpc, &fp, st);
+    if (rc) return rc;
+  }
+  const int grid = (int)nfl;
+  timing_begin(st);
+  if (acc) {
+    HB_SET_SMEM(realnvp_simt_kernel, true);
+    HB_DISPATCH_XL(realnvp_simt_kernel, true, lnpred_out, fp, n, rpc);
+  } else {
+    HB_SET_SMEM(realnvp_simt_kernel, false);
+    lp_dtype = HB_F32;
+    HB_DISPATCH_XL(realnvp_simt_kernel, false, lnpred_out, fp, n, rpc);
+  }
+  timing_end(st);
+  count_launch();
+  HB_CUDA(cudaGetLastError());
+  if (acc) return launch_merge(acc, fp, chain_lo, nfl, st);
+  return HB_OK;
+}
+
+// ---- RQSpline packing ---------------------------------------------------------------------
+int rqspline_prepare(Flow* f) {
+  const hb_flow_desc& ds = f->desc;
+  const int D = ds.ndim, K = ds.n_bins, npar = 3 * K + 1, npar_pad = pad8(npar);
+  const int nmlp = ds.n_hidden + 1;  // Dense(D), Dense(h1), ..., Dense(h_last)
+  std::vector<int> width(nmlp + 1);
+  width[0] = D;
+  width[1] = D;
+  for (int m = 0; m < ds.n_hidden; ++m) width[m + 2] = ds.hidden[m];
+  const int nact = nmlp - 1;
+  const int in_last = width[nmlp - 1];   // input width of the last MLP dense
+  const int out_last = width[nmlp];      // its output width (= input of the output dense)
+  std::vector<float> pack;
+  std::vector<RQLayer> layers(ds.n_layers);
+  auto align4 = [&]() { while (pack.size() % 4) pack.push_back(0.f); };
+  const float* w = f->host_weights.data() + 2 * (size_t)D;
+  for (int i = 0; i < ds.n_layers; ++i) {
+    RQLayer& L = layers[i];
+    std::vector<const float*> Wm(nmlp), bm(nmlp);
+    for (int m = 0; m < nmlp; ++m) {
+      Wm[m] = w;
+      w += (size_t)width[m] * width[m + 1];
+      bm[m] = w;
+      w += width[m + 1];
+    }
+    const float* Wout = w;
+    w += (size_t)out_last * D * npar;
+    const float* bout = w;
+    w += (size_t)D * npar;
+    const float* scales = w;
+    w += D;
+    const float* shifts = w;
+    w += D;
+    for (int m = 0; m < nact; ++m) {
+      const int wp = pad8(width[m + 1]);
+      align4();
+      L.w[m] = (int)pack.size();
+      for (int r = 0; r < width[m]; ++r)
+        for (int c = 0; c < wp; ++c) pack.push_back(c < width[m + 1] ? Wm[m][(size_t)r * width[m + 1] + c] : 0.f);
+      L.b[m] = (int)pack.size();
+      for (int c = 0; c < wp; ++c) pack.push_back(c < width[m + 1] ? bm[m][c] : 0.f);
+    }
+    // fused last MLP dense x output dense, per transformed feature (float64 product)
+    align4();
+    L.fused = (int)pack.size();
+    const int par = i & 1;
+    for (int j = 0; j < D; ++j) {
+      const bool visible = ((j & 1) == 1) != (par == 1);
+      if (visible) continue;
+      const float* Wl = Wm[nmlp - 1];
+      const float* bl = bm[nmlp - 1];
+      for (int r = 0; r < in_last; ++r)
+        for (int c = 0; c < npar_pad; ++c) {
+          double acc = 0.0;
+          if (c < npar)
+            for (int q = 0; q < out_last; ++q)
+              acc += (double)Wl[(size_t)r * out_last + q] * (double)Wout[(size_t)q * D * npar + (size_t)j * npar + c];
+          pack.push_back((float)acc);
+        }
+      for (int c = 0; c < npar_pad; ++c) {
+        double acc = 0.0;
+        if (c < npar) {
+          acc = bout[(size_t)j * npar + c];
+          for (int q = 0; q < out_last; ++q)
+            acc += (double)bl[q] * (double)Wout[(size_t)q * D * npar + (size_t)j * npar + c];
+        }
+        pack.push_back((float)acc);
+      }
+    }
+    align4();
+    L.scales = (int)pack.size();
+    pack.insert(pack.end(), scales, scales + D);
+    L.shifts = (int)pack.size();
+    pack.insert(pack.end(), shifts, shifts + D);
+  }
+  const size_t lay_bytes = layers.size() * sizeof(RQLayer);
+  const size_t lay_floats = (lay_bytes + 3) / 4;
+  align4();
+  const size_t lay_off = pack.size();
+  pack.resize(pack.size() + lay_floats);
+  memcpy(pack.data() + lay_off, layers.data(), lay_bytes);
+  HB_CUDA(cudaMalloc(&f->rq_pack, pack.size() * sizeof(float)));
+  HB_CUDA(cudaMemcpy(f->rq_pack, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
+  f->rq_pack_floats = pack.size();
+  f->rq_off.assign(1, lay_off);
+  return HB_OK;
+}
+
+int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                 const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                 const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                 long long b, cudaStream_t st) {
+  if (n <= 0) return HB_OK;
+  const hb_flow_desc& ds = f->desc;
+  RQParams P;
+  P.pack = f->rq_pack;
+  P.pre = ds.standardize ? f->dev_weights : nullptr;
+  P.D = ds.ndim;
+  P.K = ds.n_bins;
+  P.npar = 3 * ds.n_bins + 1;
+  P.npar_pad = pad8(P.npar);
+  P.nlayers = ds.n_layers;
+  const int nmlp = ds.n_hidden + 1;
+  P.nact = nmlp - 1;
+  P.width[0] = ds.ndim;
+  P.width[1] = ds.ndim;
+  for (int m = 0; m < ds.n_hidden; ++m) P.width[m + 2] = ds.hidden[m];
+  P.maxw = 1;
+  for (int m = 0; m <= nmlp; ++m) {
+    P.wpad[m] = pad8(P.width[m]);
+    if (m >= 1 && m <= P.nact && P.width[m] > P.maxw) P.maxw = P.width[m];
+  }
+  P.in_last = P.width[nmlp - 1];
+  P.lo = ds.range_min;
+  P.hi = ds.range_max;
+  P.T = T;
+  P.sum_log_amp = f->sum_log_amp;
+  P.layers = reinterpret_cast<const RQLayer*>(f->rq_pack + f->rq_off[0]);
+  const size_t smem = ((size_t)P.D + 2 * (size_t)P.maxw + P.npar_pad) * FT * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_error("RQSpline: ndim / hidden sizes too large for shared memory");
+    return HB_ERR_UNSUPPORTED;
+  }
+  long long nfl, rpc;
+  plan_grid(f->device, n, smem, &nfl, &rpc);
+  FoldParams fp{};
+  int rc;
+  if (acc) {
+    rc = prepare_fold(acc, start, chain_lo, chain_hi, a, b, nfl, rpc, &fp, st);
+    if (rc) return rc;
+  }
+  const int grid = (int)nfl;
+  timing_begin(st);
+  if (acc) {
+    HB_SET_SMEM(rqspline_simt_kernel, true);
+    HB_DISPATCH_XL(rqspline_simt_kernel, true, lnpred_out, fp, n, rpc);
+  } else {
+    HB_SET_SMEM(rqspline_simt_kernel, false);
+    lp_dtype = HB_F32;
+    HB_DISPATCH_XL(rqspline_simt_kernel, false, lnpred_out, fp, n, rpc);
+  }
+  timing_end(st);
+  count_launch();
+  HB_CUDA(cudaGetLastError());
+  if (acc) return launch_merge(acc, fp, chain_lo, nfl, st);
+  return HB_OK;
+}
+
+}  // namespace hb

@@ -1,0 +1,76 @@
+// Host-side internal declarations shared by the translation units of libharmonic_b200.
+#pragma once
+#include <vector>
+
+#include "hb_common.cuh"
+
+namespace hb {
+
+int require_device(int device);
+int ensure_stage(Accum* acc, size_t bytes_per_slot);
+void timing_begin(cudaStream_t st);
+void timing_end(cudaStream_t st);
+
+int ensure_scratch(Accum* acc, long long nch, long long nflushers);
+int launch_merge(Accum* acc, const FoldParams& p, long long chain_lo, long long nflushers,
+                 cudaStream_t st);
+int prepare_fold(Accum* acc, const int64_t* start, long long chain_lo, long long chain_hi,
+                 long long a, long long b, long long nflushers, long long rows_per_flusher,
+                 FoldParams* p, cudaStream_t st);
+int reset_call_scalars(Accum* acc, cudaStream_t st);
+int accumulate_precomputed_device(Accum* acc, const void* lnpred, int pd, const void* lnpost, int ld,
+                                  const int64_t* start, long long chain_lo, long long chain_hi,
+                                  long long a, long long b, cudaStream_t st);
+
+// ---- flows -------------------------------------------------------------------------------
+struct RealNVPLayerDev {
+  // SIMT layout (row-major, float32):
+  const float* W0;  // [d][128]
+  const float* b0;  // [128]
+  const float* Wt;  // [128][u]
+  const float* bt;  // [u]
+  const float* Ws;  // [128][u] or nullptr
+  const float* bs;  // [u] or nullptr
+};
+
+struct Flow {
+  hb_flow_desc desc;
+  int device = 0;
+  int path = HB_PATH_AUTO;
+  std::vector<float> host_weights;  // canonical flat buffer (header order)
+  float* dev_weights = nullptr;     // same, on device
+  float sum_log_amp = 0.f;          // sum(log(pre_amp)) (model.py:234-235)
+  // RealNVP
+  int d = 0, u = 0, nlayers = 0;
+  std::vector<size_t> layer_off;  // offset of each layer's block in the flat buffer
+  // RQSpline (re-packed, see hb_rqspline.cu)
+  float* rq_pack = nullptr;
+  std::vector<size_t> rq_off;
+  size_t rq_pack_floats = 0;
+  void* simt_params = nullptr;  // cached RealNVPSimtParams (hb_flow_simt.cu)
+  // tcgen05 image (hi/lo split, UMMA canonical layout, see hb_realnvp_tc.cu)
+  void* tc_image = nullptr;
+  size_t tc_image_bytes = 0;
+  bool tc_ok = false;
+};
+
+// kernels: evaluate lnphi for rows [0, n) of x; if acc != nullptr also fold with lnpost into acc.
+// lnpred_out may be nullptr.
+int realnvp_simt_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                     const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                     const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                     long long b, cudaStream_t st);
+int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                 const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                 const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                 long long b, cudaStream_t st);
+int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                   const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                   const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                   long long b, cudaStream_t st);
+int realnvp_tc_prepare(Flow* f);  // builds tc_image; sets tc_ok
+int rqspline_prepare(Flow* f);
+void realnvp_tc_release(Flow* f);
+void realnvp_simt_release(Flow* f);
+
+}  // namespace hb

