@@ -51,7 +51,7 @@ accumulate_precomputed_kernel(const PT* __restrict__ lnpred, const LT* __restric
   long long row_hi = row_lo + p.rows_per_flusher;
   if (row_hi > p.nrows) row_hi = p.nrows;
   const bool had_rows = row_lo < p.nrows;
-  Fold<ACC_THREADS, 0> fold(p, blockIdx.x, threadIdx.x, scratch, had_rows ? row_lo : 0);
+  Fold<ACC_THREADS> fold(p, blockIdx.x, threadIdx.x, scratch, had_rows ? row_lo : 0);
   for (long long t0 = row_lo; t0 < row_hi; t0 += ACC_TILE) {
     long long t1 = t0 + ACC_TILE;
     float a[ACC_R], b[ACC_R];

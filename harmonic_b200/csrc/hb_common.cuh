@@ -67,12 +67,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ float nanmaxf(float a, float b) { return fmaxf(a, b); }  // fmaxf drops NaN
 __device__ __forceinline__ float nanminf(float a, float b) { return fminf(a, b); }
 
-// Fold: every thread of a "flusher" group (NT threads synchronised on named barrier BAR) feeds
+// Fold: every thread of a "flusher" group (NT threads synchronised on a named barrier) feeds
 // the rows it owns; rows of one flusher are a contiguous range, walked tile by tile in order.
 // Implements lnarg = lnpred - lnpost, +-inf -> NaN (harmonic/evidence.py:278-283), NaN counting
 // (:342-345), the per-chain sums (:321-334, as a max-rescaled online logsumexp) and the six
 // nan-aware extrema + mean-shift sums (:307-319,347-352).
-template <int NT, int BAR>
+template <int NT>
 struct Fold {
   // uniform across the group
   const FoldParams& p;
@@ -80,6 +80,7 @@ struct Fold {
   int cur_chain;
   long long cur_end;  // local row where cur_chain ends
   int tid;            // 0..NT-1 within the group
+  int bar;            // named barrier id private to the group (0 = whole CTA when NT == blockDim)
   double* scratch;    // shared, >= 3*(NT/32) doubles, private to the group
   // per thread
   float m, s;
@@ -88,8 +89,9 @@ struct Fold {
   int gcnt;
   float amax, amin, pmax, pmin, qmax, qmin;
 
-  __device__ Fold(const FoldParams& p_, int flusher_, int tid_, double* scratch_, long long row_lo)
-      : p(p_), flusher(flusher_), tid(tid_), scratch(scratch_) {
+  __device__ Fold(const FoldParams& p_, int flusher_, int tid_, double* scratch_, long long row_lo,
+                  int bar_ = 0)
+      : p(p_), flusher(flusher_), tid(tid_), bar(bar_), scratch(scratch_) {
     m = -CUDART_INF_F;
     s = 0.f;
     nnan = 0;
@@ -151,7 +153,7 @@ struct Fold {
       scratch[(tid >> 5) * 3 + 1] = sw;
       scratch[(tid >> 5) * 3 + 2] = (double)nw;
     }
-    named_bar_sync(BAR, NT);
+    named_bar_sync(bar, NT);
     if (tid == 0) {
       double M = -CUDART_INF, S = 0.0, NN = 0.0;
       for (int w = 0; w < NW; ++w) M = fmax(M, scratch[w * 3]);
@@ -167,7 +169,7 @@ struct Fold {
       r.valid = 1.0;
       p.recs[cur_chain + flusher] = r;
     }
-    named_bar_sync(BAR, NT);
+    named_bar_sync(bar, NT);
     m = -CUDART_INF_F;
     s = 0.f;
     nnan = 0;
@@ -217,12 +219,12 @@ struct Fold {
       }
     }
     // scratch holds 3*NW doubles; reuse it in three rounds of (sum,cnt | extrema)
-    named_bar_sync(BAR, NT);
+    named_bar_sync(bar, NT);
     double out[G_N];
     for (int k = 0; k < G_N; ++k) {
       double mine = (k == 0) ? gs : (k == 1) ? gc : (double)v[k - 2];
       if ((tid & 31) == 0) scratch[tid >> 5] = mine;
-      named_bar_sync(BAR, NT);
+      named_bar_sync(bar, NT);
       if (tid == 0) {
         double acc = scratch[0];
         for (int w = 1; w < NW; ++w) {
@@ -233,7 +235,7 @@ struct Fold {
         }
         out[k] = acc;
       }
-      named_bar_sync(BAR, NT);
+      named_bar_sync(bar, NT);
     }
     if (tid == 0) {
       for (int k = 0; k < G_N; ++k) p.gpart[(long long)flusher * G_N + k] = out[k];

@@ -91,7 +91,7 @@ realnvp_simt_kernel(RealNVPSimtParams P, const XT* __restrict__ x, long long ld,
   long long row_hi = row_lo + rows_per_cta;
   if (row_hi > nrows) row_hi = nrows;
   const bool had_rows = row_lo < nrows;
-  Fold<FT, 0> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
+  Fold<FT> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
   const float invT = 1.f / P.T;
   const float base_const = -(float)D * logf(P.T) - 0.5f * (float)D * 1.8378770664093453f;
 
@@ -252,7 +252,7 @@ rqspline_simt_kernel(RQParams P, const XT* __restrict__ x, long long ld,
   long long row_hi = row_lo + rows_per_cta;
   if (row_hi > nrows) row_hi = nrows;
   const bool had_rows = row_lo < nrows;
-  Fold<FT, 0> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
+  Fold<FT> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
   const float base_const = -0.5f * (float)D * 1.8378770664093453f - 0.5f * (float)D * logf(P.T);
   auto ident = [](int i) { return i; };
   auto all = [](int) { return true; };

@@ -33,7 +33,7 @@ def test_realnvp_predict_simt(ndim, standardize):
 
 @pytest.mark.parametrize("layers", [(1, 0), (6, 2), (3, 5)])
 def test_realnvp_layer_counts_and_temperature(layers):
-    m = util.make_realnvp(5, layers[0], layers[1], seed=7)
+    m = util.make_realnvp(5, layers[0], layers[1], seed=7, ws=0.4)
     m.kernel_path = _lib.HB_PATH_SIMT
     x = samples(777, 5, seed=2)
     for T in (1.0, 0.9, 0.3):
@@ -133,3 +133,41 @@ def test_fused_device_resident_f32_matches_host():
     p = m.predict(xs)
     assert p.is_cuda and p.shape == (16000,)
     util.assert_lnphi_close(p.cpu().numpy(), util.oracle_predict(m, ch.samples.astype(np.float32)))
+
+
+# ------------------------------------------------------------------ tcgen05 path (ndim = 64)
+@pytest.mark.parametrize("standardize", [False, True])
+@pytest.mark.parametrize("n", [1, 127, 128, 1000, 70000])
+def test_realnvp_tcgen05_predict(standardize, n):
+    m = util.make_realnvp(64, seed=5, standardize=standardize, ws=0.5)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = samples(n, 64, seed=6, scale=1.2)
+    got = m.predict(x)
+    want = util.oracle_predict(m, x)
+    util.assert_lnphi_close(got, want)
+    m2 = util.make_realnvp(64, seed=5, standardize=standardize, ws=0.5)
+    m2.kernel_path = _lib.HB_PATH_SIMT
+    util.assert_lnphi_close(got, m2.predict(x).astype(np.float64), rel=2e-6)
+
+
+@pytest.mark.parametrize("layers", [(1, 0), (2, 4), (3, 1)])
+def test_realnvp_tcgen05_layers_nan(layers):
+    m = util.make_realnvp(64, layers[0], layers[1], seed=8, ws=0.5, temperature=0.6)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = samples(3000, 64, seed=7)
+    x[11, 3] = np.nan
+    x[12, 40] = np.nan
+    got = m.predict(x.astype(np.float32))
+    util.assert_lnphi_close(got, util.oracle_predict(m, x.astype(np.float32)))
+    assert np.isnan(got[11]) and np.isnan(got[12])
+
+
+def test_realnvp_tcgen05_fused_vs_oracle_and_auto_path():
+    m = util.make_realnvp(64, seed=9, standardize=True, ws=0.3)
+    lib = _lib.load()
+    assert lib.hb_flow_uses_tcgen05(m._get_handle()) == 1  # AUTO picks the tensor path at ndim 64
+    ch = util.gaussian_chains(64, 24, 900, seed=3, ragged=True)
+    ev = hm.Evidence(ch.nchains, m)
+    ev.add_chains(ch)
+    ref = util.oracle_evidence(m, ch)
+    util.assert_evidence_close(ev, ref)
