@@ -24,9 +24,9 @@ def test_realnvp_predict_simt(ndim, standardize):
     x = samples(1000, ndim, seed=1, scale=1.5)
     got = m.predict(x)
     assert got.dtype == np.float32 and got.shape == (1000,)
-    util.assert_lnphi_close(got, util.oracle_predict(m, x))
+    util.check_predict(m, x, got)
     # float32 input gives the same answer; 1-D input gives a scalar (model.py:229-231)
-    util.assert_lnphi_close(m.predict(x.astype(np.float32)), util.oracle_predict(m, x.astype(np.float32)))
+    util.check_predict(m, x.astype(np.float32), m.predict(x.astype(np.float32)))
     assert np.ndim(m.predict(x[0])) == 0
     assert float(m.predict(x[0])) == pytest.approx(float(got[0]), rel=1e-6)
 
@@ -38,7 +38,7 @@ def test_realnvp_layer_counts_and_temperature(layers):
     x = samples(777, 5, seed=2)
     for T in (1.0, 0.9, 0.3):
         m.temperature = T  # runtime-mutable, read on every call (model.py:214)
-        util.assert_lnphi_close(m.predict(x), util.oracle_predict(m, x))
+        util.check_predict(m, x, m.predict(x))
     m.temperature = 1.5
     with pytest.raises(ValueError):
         m.predict(x)
@@ -57,13 +57,13 @@ def test_rqspline_predict(ndim, hidden, layers, standardize):
     x[5, 0] = 10.0
     x[6, ndim - 1] = -10.0
     got = m.predict(x)
-    util.assert_lnphi_close(got, util.oracle_predict(m, x))
+    util.check_predict(m, x, got)
 
 
 def test_rqspline_bins_and_range():
     m = util.make_rqspline(3, 2, 5, (16, 16), seed=11, spline_range=(-3.0, 4.0), temperature=0.5)
     x = samples(800, 3, seed=4, scale=2.5)
-    util.assert_lnphi_close(m.predict(x), util.oracle_predict(m, x))
+    util.check_predict(m, x, m.predict(x))
 
 
 @pytest.mark.parametrize("kind", ["realnvp", "rqspline"])
@@ -143,8 +143,7 @@ def test_realnvp_tcgen05_predict(standardize, n):
     m.kernel_path = _lib.HB_PATH_TCGEN05
     x = samples(n, 64, seed=6, scale=1.2)
     got = m.predict(x)
-    want = util.oracle_predict(m, x)
-    util.assert_lnphi_close(got, want)
+    util.check_predict(m, x, got)
     m2 = util.make_realnvp(64, seed=5, standardize=standardize, ws=0.5)
     m2.kernel_path = _lib.HB_PATH_SIMT
     util.assert_lnphi_close(got, m2.predict(x).astype(np.float64), rel=2e-6)
@@ -158,7 +157,7 @@ def test_realnvp_tcgen05_layers_nan(layers):
     x[11, 3] = np.nan
     x[12, 40] = np.nan
     got = m.predict(x.astype(np.float32))
-    util.assert_lnphi_close(got, util.oracle_predict(m, x.astype(np.float32)))
+    util.check_predict(m, x.astype(np.float32), got)
     assert np.isnan(got[11]) and np.isnan(got[12])
 
 
