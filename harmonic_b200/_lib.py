@@ -110,11 +110,18 @@ def check(rc):
     raise HarmonicB200Error(msg)
 
 
+_gpu_ok = False
+
+
 def require_gpu():
+    global _gpu_ok
     lib = load()
+    if _gpu_ok:
+        return lib
     if lib.hb_device_count() < 1:
         raise HarmonicB200Error(
             "no sm_100 (B200) device visible: harmonic_b200 has no CPU fallback")
+    _gpu_ok = True
     return lib
 
 

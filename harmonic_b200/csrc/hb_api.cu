@@ -41,6 +41,9 @@ void timing_end(cudaStream_t st) {
 }
 
 int require_device(int device) {
+  // cudaGetDeviceProperties costs milliseconds per call; remember devices already validated
+  static std::atomic<unsigned long long> ok_mask{0};
+  if (device >= 0 && device < 64 && ((ok_mask.load() >> device) & 1ull)) return HB_OK;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0) {
@@ -59,6 +62,7 @@ int require_device(int device) {
               "; libharmonic_b200 is built for sm_100a only");
     return HB_ERR_NO_DEVICE;
   }
+  if (device < 64) ok_mask.fetch_or(1ull << device);
   return HB_OK;
 }
 
@@ -101,6 +105,8 @@ int hb_version(void) { return HB_VERSION; }
 const char* hb_last_error(void) { return g_err.c_str(); }
 
 int hb_device_count(void) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
     cudaGetLastError();
@@ -111,6 +117,7 @@ int hb_device_count(void) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++ok;
   }
+  if (ok > 0) cached = ok;
   return ok;
 }
 

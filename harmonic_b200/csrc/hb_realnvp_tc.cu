@@ -16,9 +16,11 @@
 //                                E2     shift/scale epilogue on y1, log-det
 // Each GEMM is 3xTF32: a.w ~= a_lo.w_hi + a_hi.w_lo + a_hi.w_hi with FP32 accumulation in TMEM
 // (hi = top 19 bits, lo = exact remainder), so per-sample ln phi keeps ~FP32 accuracy.
-// TMEM (512 columns): P0 | P1 (H -> h_hi in place, per tile) | Q (h_lo, shared by both tiles) |
-// O0 | O1 (GEMM2 accumulators).  The two tiles run half a layer apart so the tensor pipe works on
-// one while the CUDA cores run the other's epilogue.
+// TMEM (512 columns), per tile t at column 256 t:  P (128: H, then h_hi in place) | Q (64: h_lo of
+// the hidden half in flight) | O (64: GEMM2 accumulators).  GEMM2 runs as two K-halves so that only
+// half of h_lo has to live in TMEM; the epilogue of the second half overlaps the first half's MMAs.
+// The MMA thread issues whichever tile's next GEMM is ready (layers stay in lock-step so that the
+// weight ring is consumed in order), so one tile's epilogue overlaps the other tile's tensor work.
 #include <math.h>
 #include <string.h>
 
@@ -45,15 +47,19 @@ constexpr int MAX_TC_LAYERS = 16;
 constexpr int SM_RING = 0;
 constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;            // per WG: hi 16 KB | lo 16 KB
 constexpr int SM_BIAS = SM_A1 + NWG * 32768;                    // MAX_TC_LAYERS * 192 floats
-constexpr int SM_BAR = SM_BIAS + MAX_TC_LAYERS * 192 * 4;       // mbarriers
+constexpr int SM_PRE = SM_BIAS + MAX_TC_LAYERS * 192 * 4;       // standardisation: inv_amp[D], -offset*inv_amp[D]
+constexpr int SM_BAR = SM_PRE + 2 * D * 4;                      // mbarriers
 constexpr int SM_MISC = SM_BAR + 256;                           // tmem ptr, fold scratch
 constexpr int SM_TOTAL = SM_MISC + 256;
 
 // barrier indices (8 bytes each)
-enum { B_WFULL = 0, B_WEMPTY = 4, B_A1FULL = 8, B_HFULL = 10, B_A2FULL = 12, B_OFULL = 14, B_COUNT = 16 };
+enum {
+  B_WFULL = 0, B_WEMPTY = 4, B_A1FULL = 8, B_HFULL = 10, B_A2A = 12, B_QFREE = 14, B_A2B = 16, B_OFULL = 18,
+  B_COUNT = 20
+};
 
-// TMEM columns
-constexpr uint32_t TM_P0 = 0, TM_Q = 256, TM_O0 = 384;
+// TMEM columns (per tile: + 256 * tile)
+constexpr uint32_t TM_P = 0, TM_Q = 128, TM_O = 192, TM_TILE = 256;
 
 struct Params {
   const uint8_t* image;   // weight image: chunks of SLOT_BYTES in consumption order
@@ -219,6 +225,59 @@ __device__ __forceinline__ void load_row<double>(const double* __restrict__ x, l
   }
 }
 
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// clip(softplus(a), 1e-3, 1e3) with MUFU ex2/lg2 (harmonic/flows.py:177).  t = exp(-|a|) in (0, 1];
+// log1p(t) by a 4-term series below 0.06 (rel. err < 3e-6) and ln2 * lg2(1 + t) above.
+__device__ __forceinline__ float softplus_clip_fast(float a) {
+  const float t = ex2_approx(-1.4426950408889634f * fabsf(a));
+  const float series = t * fmaf(t, fmaf(t, fmaf(t, -0.25f, 0.33333334f), -0.5f), 1.0f);
+  const float via_log = 0.6931471805599453f * lg2_approx(1.0f + t);
+  const float sp = fmaxf(a, 0.f) + ((t < 0.06f) ? series : via_log);
+  return fminf(fmaxf(sp, 1e-3f), 1e3f);  // NaN in -> NaN out is handled by the caller's y1 path
+}
+
+// E1 for one 32-column chunk: h = leaky_relu(H + b0) -> hi (top 19 bits) / lo (exact remainder)
+__device__ __forceinline__ void e1_chunk(uint32_t (&v)[32], uint32_t (&w)[32], const float* b0c) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float h = __uint_as_float(v[j]) + b0c[j];
+    h = fmaxf(h, 0.01f * h);
+    const uint32_t hb = __float_as_uint(h) & 0xffffe000u;
+    v[j] = hb;
+    w[j] = __float_as_uint(h - __uint_as_float(hb));
+  }
+}
+
 template <typename XT, typename LT, bool FOLD>
 __global__ void __launch_bounds__(THREADS, 1)
 realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __restrict__ lnpost,
@@ -231,6 +290,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + SM_MISC);
   float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS);
+  float* pre_s = reinterpret_cast<float*>(smem + SM_PRE);
   const int nl = P.nlayers;
 
   // ---- one-time setup -------------------------------------------------------------------
@@ -242,12 +302,19 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     for (int t = 0; t < NWG; ++t) {
       mbar_init(BAR(B_A1FULL + t), 128);
       mbar_init(BAR(B_HFULL + t), 1);
-      mbar_init(BAR(B_A2FULL + t), 128);
+      mbar_init(BAR(B_A2A + t), 128);
+      mbar_init(BAR(B_QFREE + t), 1);
+      mbar_init(BAR(B_A2B + t), 128);
       mbar_init(BAR(B_OFULL + t), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < nl * 192; i += THREADS) bias_s[i] = P.bias[i];
+  for (int i = threadIdx.x; i < D; i += THREADS) {
+    const float inv = P.pre ? 1.f / P.pre[D + i] : 1.f;
+    pre_s[i] = inv;
+    pre_s[D + i] = P.pre ? -P.pre[i] * inv : 0.f;
+  }
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void*)tmem_ptr)),
@@ -279,7 +346,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       }
     }
   } else if (warp == 9) {
-    // ===== MMA issuer (one thread) =====
+    // ===== MMA issuer (one thread); within a layer it serves whichever tile is ready =====
     if (lane == 0) {
       const uint32_t id128 = make_idesc(128), id64 = make_idesc(64), id32 = make_idesc(32);
       uint32_t g = 0, it = 0;
@@ -287,63 +354,77 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         for (int l = 0; l < nl; ++l, ++it) {
           const bool scaled = l < P.nscaled;
           const uint32_t par = it & 1;
-          // ---- GEMM1 for both tiles: H = y0 . W0 (K = 32 -> 4 k-steps, three split passes)
           const uint32_t s0 = g & (NSLOTS - 1);
-          mbar_wait(BAR(B_WFULL + s0), (g / NSLOTS) & 1);
+          const uint32_t s1 = (g + 1) & (NSLOTS - 1), s2 = (g + 2) & (NSLOTS - 1);
           const uint32_t w0 = sbase + SM_RING + s0 * SLOT_BYTES;  // hi [128x32] 16 KB | lo 16 KB
-          for (int t = 0; t < NWG; ++t) {
-            mbar_wait(BAR(B_A1FULL + t), par);
-            tc_fence_after();
-            const uint32_t a_hi = sbase + SM_A1 + t * 32768, a_lo = a_hi + 16384;
-            const uint32_t dcol = tmem_base + TM_P0 + t * 128;
-            uint32_t acc = 0;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t aa = (pass == 0) ? a_lo : a_hi;
-              const uint32_t bb = (pass == 1) ? w0 + 16384 : w0;
-#pragma unroll
-              for (int k = 0; k < DH / 8; ++k) {
-                mma_ss(dcol, make_desc(aa + k * 4096, 2048, 128), make_desc(bb + k * 4096, 2048, 128), id128, acc);
-                acc = 1;
-              }
-            }
-            tc_commit(BAR(B_HFULL + t));
-          }
-          tc_commit(BAR(B_WEMPTY + s0));
-          ++g;
-          // ---- GEMM2 for both tiles: O = h . [Wt|Ws] (K = 128 -> 16 k-steps, A from TMEM)
-          const uint32_t s1 = g & (NSLOTS - 1), s2 = (g + 1) & (NSLOTS - 1);
-          mbar_wait(BAR(B_WFULL + s1), (g / NSLOTS) & 1);
-          if (scaled) mbar_wait(BAR(B_WFULL + s2), ((g + 1) / NSLOTS) & 1);
-          const uint32_t n2 = scaled ? 64 : 32;
-          const uint32_t lbo2 = n2 * 16;
+          const uint32_t lbo2 = (scaled ? 64u : 32u) * 16u;
           const uint32_t w_hi = sbase + SM_RING + s1 * SLOT_BYTES;
           const uint32_t w_lo = scaled ? sbase + SM_RING + s2 * SLOT_BYTES : w_hi + 16384;
           const uint32_t id2 = scaled ? id64 : id32;
-          for (int t = 0; t < NWG; ++t) {
-            mbar_wait(BAR(B_A2FULL + t), par);
-            tc_fence_after();
-            const uint32_t p_hi = tmem_base + TM_P0 + t * 128, p_lo = tmem_base + TM_Q;
-            const uint32_t dcol = tmem_base + TM_O0 + t * 64;
-            uint32_t acc = 0;
+          const uint64_t wd_hi = make_desc(w0, 2048, 128), wd_lo = make_desc(w0 + 16384, 2048, 128);
+          const uint64_t bd_hi = make_desc(w_hi, lbo2, 128), bd_lo = make_desc(w_lo, lbo2, 128);
+          const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
+          mbar_wait(BAR(B_WFULL + s0), (g / NSLOTS) & 1);
+          bool w2_ready = false, w0_released = false;
+          int stage0 = 0, stage1 = 0;  // 0: GEMM1, 1: GEMM2 first half, 2: GEMM2 second half, 3: done
+          while (stage0 < 3 || stage1 < 3) {
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t aa = (pass == 0) ? p_lo : p_hi;
-              const uint32_t bb = (pass == 1) ? w_lo : w_hi;
-#pragma unroll 4
-              for (int k = 0; k < HID / 8; ++k) {
-                mma_ts(dcol, aa + k * 8, make_desc(bb + k * 2 * lbo2, lbo2, 128), id2, acc);
-                acc = 1;
+            for (int t = 0; t < NWG; ++t) {
+              const int stage = t ? stage1 : stage0;
+              const uint32_t tb = tmem_base + t * TM_TILE;
+              if (stage == 0) {
+                if (!mbar_test(BAR(B_A1FULL + t), par)) continue;
+                tc_fence_after();
+                // GEMM1: H = y0 . W0 (K = 32 -> 4 k-steps, three split passes, small terms first)
+                const uint32_t a_hi = sbase + SM_A1 + t * 32768;
+                const uint64_t ad_hi = make_desc(a_hi, 2048, 128), ad_lo = make_desc(a_hi + 16384, 2048, 128);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                  const uint64_t aa = (pass == 0) ? ad_lo : ad_hi;
+                  const uint64_t bb = (pass == 1) ? wd_lo : wd_hi;
+#pragma unroll
+                  for (int k = 0; k < DH / 8; ++k) {
+                    mma_ss(tb + TM_P, aa + (uint64_t)(k * 256), bb + (uint64_t)(k * 256), id128, acc);
+                    acc = 1;
+                  }
+                }
+                tc_commit(BAR(B_HFULL + t));
+              } else if (stage <= 2) {
+                const int half = stage - 1;
+                if (!mbar_test(BAR((half ? B_A2B : B_A2A) + t), par)) continue;
+                if (!w2_ready) {
+                  mbar_wait(BAR(B_WFULL + s1), ((g + 1) / NSLOTS) & 1);
+                  if (scaled) mbar_wait(BAR(B_WFULL + s2), ((g + 2) / NSLOTS) & 1);
+                  w2_ready = true;
+                }
+                tc_fence_after();
+                // GEMM2 half: O (+)= h[:, 64 half ..] . W2[64 half .., :]  (A from TMEM, K = 64)
+                uint32_t acc = half ? 1u : 0u;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                  const uint32_t aa = (pass == 0) ? tb + TM_Q : tb + TM_P + half * 64;
+                  const uint64_t bb = ((pass == 1) ? bd_lo : bd_hi) + (uint64_t)(half * 8) * kstep2;
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    mma_ts(tb + TM_O, aa + k * 8, bb + (uint64_t)k * kstep2, id2, acc);
+                    acc = 1;
+                  }
+                }
+                tc_commit(BAR((half ? B_OFULL : B_QFREE) + t));
+              } else {
+                continue;
               }
+              if (t) ++stage1; else ++stage0;
             }
-            tc_commit(BAR(B_OFULL + t));
+            if (!w0_released && stage0 >= 1 && stage1 >= 1) {  // both GEMM1s issued: free W0's slot
+              tc_commit(BAR(B_WEMPTY + s0));
+              w0_released = true;
+            }
           }
           tc_commit(BAR(B_WEMPTY + s1));
-          ++g;
-          if (scaled) {
-            tc_commit(BAR(B_WEMPTY + s2));
-            ++g;
-          }
+          if (scaled) tc_commit(BAR(B_WEMPTY + s2));
+          g += scaled ? 3 : 2;
         }
       }
     }
@@ -352,9 +433,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     const int wg = warp >> 2;              // 0 / 1
     const int tid = threadIdx.x & 127;     // TMEM lane == sample row within the tile
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    const uint32_t tm_p = tmem_base + lane_base + TM_P0 + wg * 128;
-    const uint32_t tm_q = tmem_base + lane_base + TM_Q;
-    const uint32_t tm_o = tmem_base + lane_base + TM_O0 + wg * 64;
+    const uint32_t tm_p = tmem_base + lane_base + wg * TM_TILE + TM_P;
+    const uint32_t tm_q = tmem_base + lane_base + wg * TM_TILE + TM_Q;
+    const uint32_t tm_o = tmem_base + lane_base + wg * TM_TILE + TM_O;
     uint8_t* a1 = smem + SM_A1 + wg * 32768;
     double* scratch = reinterpret_cast<double*>(smem + SM_MISC + 16) + wg * 12;
     const int flusher = blockIdx.x * NWG + wg;
@@ -375,10 +456,13 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       const long long rr = live ? r : 0;
       float y[D];
       load_row<XT>(x, ld, rr, y);
-      if (P.pre) {
+      if (r + TILE < row_hi) {  // pull the next tile's row into L2 while this tile computes
+        const char* nx = reinterpret_cast<const char*>(x + (r + TILE) * ld);
 #pragma unroll
-        for (int i = 0; i < D; ++i) y[i] = (y[i] - __ldg(P.pre + i)) / __ldg(P.pre + D + i);
+        for (int q = 0; q < (int)(D * sizeof(XT)); q += 128) prefetch_l2(nx + q);
       }
+#pragma unroll
+      for (int i = 0; i < D; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
       float ldj = 0.f;
       for (int l = 0; l < nl; ++l, ++it) {
         const uint32_t par = it & 1;
@@ -402,31 +486,41 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           *reinterpret_cast<uint4*>(a1 + 16384 + c * 2048 + tid * 16) = lo;
         }
         fence_proxy_async();
-        tc_fence_before();
+        tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
         mbar_arrive(BAR(B_A1FULL + wg));
-        // ---- E1: h = leaky_relu(H + b0) -> (hi in place, lo into Q)
+        // ---- E1: h = leaky_relu(H + b0) -> hi in place, lo into Q; two 64-column halves
         mbar_wait(BAR(B_HFULL + wg), par);
-        if (wg == 1) mbar_wait(BAR(B_OFULL + 0), par);  // Q is still GEMM2(tile 0)'s operand until then
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < HID / 32; ++c) {
+        {
           uint32_t v[32], w[32];
-          tmem_ld32(tm_p + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float h = __uint_as_float(v[j]) + b0[c * 32 + j];
-            h = fmaxf(h, 0.01f * h);
-            const uint32_t hb = __float_as_uint(h) & 0xffffe000u;
-            v[j] = hb;
-            w[j] = __float_as_uint(h - __uint_as_float(hb));
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {  // first hidden half
+            tmem_ld32(tm_p + c * 32, v);
+            tmem_ld_wait();
+            e1_chunk(v, w, b0 + c * 32);
+            tmem_st32(tm_p + c * 32, v);
+            tmem_st32(tm_q + c * 32, w);
           }
-          tmem_st32(tm_p + c * 32, v);
-          tmem_st32(tm_q + c * 32, w);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(BAR(B_A2A + wg));
+          // second half: compute chunk 2 while GEMM2's first half still reads Q
+          tmem_ld32(tm_p + 64, v);
+          tmem_ld_wait();
+          e1_chunk(v, w, b0 + 64);
+          tmem_st32(tm_p + 64, v);
+          mbar_wait(BAR(B_QFREE + wg), par);
+          tc_fence_after();
+          tmem_st32(tm_q, w);
+          tmem_ld32(tm_p + 96, v);
+          tmem_ld_wait();
+          e1_chunk(v, w, b0 + 96);
+          tmem_st32(tm_p + 96, v);
+          tmem_st32(tm_q + 32, w);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(BAR(B_A2B + wg));
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(BAR(B_A2FULL + wg));
         // ---- E2: y1 = (y1 - shift) / scale, ldj -= sum log scale
         mbar_wait(BAR(B_OFULL + wg), par);
         tc_fence_after();
@@ -438,11 +532,18 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             tmem_ld32(tm_o + 32, sc);
             tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-              const float shift = __uint_as_float(sh[k]) + b2[k];
-              const float s = softplus_clip(__uint_as_float(sc[k]) + b2[U + k]);
-              y[DH + k] = (y[DH + k] - shift) / s;
-              ldj -= logf(s);
+            for (int k0 = 0; k0 < U; k0 += 8) {
+              float prod = 1.f;  // 8 factors in [1e-3, 1e3] stay inside the float32 range
+#pragma unroll
+              for (int k = k0; k < k0 + 8; ++k) {
+                const float shift = __uint_as_float(sh[k]) + b2[k];
+                const float a = __uint_as_float(sc[k]) + b2[U + k];
+                float s = softplus_clip_fast(a);
+                s = (a != a) ? a : s;  // keep NaN (fminf/fmaxf would drop it)
+                y[DH + k] = (y[DH + k] - shift) * rcp_approx(s);
+                prod *= s;
+              }
+              ldj -= 0.6931471805599453f * lg2_approx(prod);
             }
           } else {
             tmem_ld_wait();
@@ -471,9 +572,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         float bb[1] = {live ? (float)lnpost[r] : 0.f};
         long long t1 = t0 + TILE;
         if (t1 > row_hi) t1 = row_hi;
-        if (t0 < row_hi) {
-          fold.tile<1>(t0, t1, a, bb);
-        }
+        if (t0 < row_hi) fold.tile<1>(t0, t1, a, bb);
       }
     }
     if (FOLD) fold.finish(had_rows);
