@@ -238,6 +238,17 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -346,38 +357,41 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       }
     }
   } else if (warp == 9) {
-    // ===== MMA issuer (one thread); within a layer it serves whichever tile is ready =====
-    if (lane == 0) {
-      const uint32_t id128 = make_idesc(128), id64 = make_idesc(64), id32 = make_idesc(32);
-      uint32_t g = 0, it = 0;
-      for (int b = 0; b < P.nbatches; ++b) {
-        for (int l = 0; l < nl; ++l, ++it) {
-          const bool scaled = l < P.nscaled;
-          const uint32_t par = it & 1;
-          const uint32_t s0 = g & (NSLOTS - 1);
-          const uint32_t s1 = (g + 1) & (NSLOTS - 1), s2 = (g + 2) & (NSLOTS - 1);
-          const uint32_t w0 = sbase + SM_RING + s0 * SLOT_BYTES;  // hi [128x32] 16 KB | lo 16 KB
-          const uint32_t lbo2 = (scaled ? 64u : 32u) * 16u;
-          const uint32_t w_hi = sbase + SM_RING + s1 * SLOT_BYTES;
-          const uint32_t w_lo = scaled ? sbase + SM_RING + s2 * SLOT_BYTES : w_hi + 16384;
-          const uint32_t id2 = scaled ? id64 : id32;
-          const uint64_t wd_hi = make_desc(w0, 2048, 128), wd_lo = make_desc(w0 + 16384, 2048, 128);
-          const uint64_t bd_hi = make_desc(w_hi, lbo2, 128), bd_lo = make_desc(w_lo, lbo2, 128);
-          const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
-          mbar_wait(BAR(B_WFULL + s0), (g / NSLOTS) & 1);
-          bool w2_ready = false, w0_released = false;
-          int stage0 = 0, stage1 = 0;  // 0: GEMM1, 1: GEMM2 first half, 2: GEMM2 second half, 3: done
-          while (stage0 < 3 || stage1 < 3) {
+    // ===== MMA issuer: the whole warp runs the (warp-uniform) scheduling loop so that descriptors
+    // stay in uniform registers; one elected lane issues.  Within a layer it serves whichever
+    // tile is ready.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t id128 = make_idesc(128), id64 = make_idesc(64), id32 = make_idesc(32);
+    uint32_t g = 0, it = 0;
+    for (int b = 0; b < P.nbatches; ++b) {
+      for (int l = 0; l < nl; ++l, ++it) {
+        const bool scaled = l < P.nscaled;
+        const uint32_t par = it & 1;
+        const uint32_t s0 = g & (NSLOTS - 1);
+        const uint32_t s1 = (g + 1) & (NSLOTS - 1), s2 = (g + 2) & (NSLOTS - 1);
+        const uint32_t w0 = sbase + SM_RING + s0 * SLOT_BYTES;  // hi [128x32] 16 KB | lo 16 KB
+        const uint32_t lbo2 = (scaled ? 64u : 32u) * 16u;
+        const uint32_t w_hi = sbase + SM_RING + s1 * SLOT_BYTES;
+        const uint32_t w_lo = scaled ? sbase + SM_RING + s2 * SLOT_BYTES : w_hi + 16384;
+        const uint32_t id2 = scaled ? id64 : id32;
+        const uint64_t wd_hi = make_desc(w0, 2048, 128), wd_lo = make_desc(w0 + 16384, 2048, 128);
+        const uint64_t bd_hi = make_desc(w_hi, lbo2, 128), bd_lo = make_desc(w_lo, lbo2, 128);
+        const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
+        mbar_wait(BAR(B_WFULL + s0), (g / NSLOTS) & 1);
+        bool w2_ready = false, w0_released = false;
+        int stage0 = 0, stage1 = 0;  // 0: GEMM1, 1: GEMM2 first half, 2: GEMM2 second half, 3: done
+        while (stage0 < 3 || stage1 < 3) {
 #pragma unroll
-            for (int t = 0; t < NWG; ++t) {
-              const int stage = t ? stage1 : stage0;
-              const uint32_t tb = tmem_base + t * TM_TILE;
-              if (stage == 0) {
-                if (!mbar_test(BAR(B_A1FULL + t), par)) continue;
-                tc_fence_after();
-                // GEMM1: H = y0 . W0 (K = 32 -> 4 k-steps, three split passes, small terms first)
-                const uint32_t a_hi = sbase + SM_A1 + t * 32768;
-                const uint64_t ad_hi = make_desc(a_hi, 2048, 128), ad_lo = make_desc(a_hi + 16384, 2048, 128);
+          for (int t = 0; t < NWG; ++t) {
+            const int stage = t ? stage1 : stage0;
+            const uint32_t tb = tmem_u + t * TM_TILE;
+            if (stage == 0) {
+              if (!__all_sync(0xffffffffu, mbar_test(BAR(B_A1FULL + t), par))) continue;
+              tc_fence_after();
+              // GEMM1: H = y0 . W0 (K = 32 -> 4 k-steps, three split passes, small terms first)
+              const uint32_t a_hi = sbase + SM_A1 + t * 32768;
+              const uint64_t ad_hi = make_desc(a_hi, 2048, 128), ad_lo = make_desc(a_hi + 16384, 2048, 128);
+              if (elect_one()) {
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -390,16 +404,19 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
                   }
                 }
                 tc_commit(BAR(B_HFULL + t));
-              } else if (stage <= 2) {
-                const int half = stage - 1;
-                if (!mbar_test(BAR((half ? B_A2B : B_A2A) + t), par)) continue;
-                if (!w2_ready) {
-                  mbar_wait(BAR(B_WFULL + s1), ((g + 1) / NSLOTS) & 1);
-                  if (scaled) mbar_wait(BAR(B_WFULL + s2), ((g + 2) / NSLOTS) & 1);
-                  w2_ready = true;
-                }
-                tc_fence_after();
-                // GEMM2 half: O (+)= h[:, 64 half ..] . W2[64 half .., :]  (A from TMEM, K = 64)
+              }
+              __syncwarp();
+            } else if (stage <= 2) {
+              const int half = stage - 1;
+              if (!__all_sync(0xffffffffu, mbar_test(BAR((half ? B_A2B : B_A2A) + t), par))) continue;
+              if (!w2_ready) {
+                mbar_wait(BAR(B_WFULL + s1), ((g + 1) / NSLOTS) & 1);
+                if (scaled) mbar_wait(BAR(B_WFULL + s2), ((g + 2) / NSLOTS) & 1);
+                w2_ready = true;
+              }
+              tc_fence_after();
+              // GEMM2 half: O (+)= h[:, 64 half ..] . W2[64 half .., :]  (A from TMEM, K = 64)
+              if (elect_one()) {
                 uint32_t acc = half ? 1u : 0u;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -412,20 +429,25 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
                   }
                 }
                 tc_commit(BAR((half ? B_OFULL : B_QFREE) + t));
-              } else {
-                continue;
               }
-              if (t) ++stage1; else ++stage0;
+              __syncwarp();
+            } else {
+              continue;
             }
-            if (!w0_released && stage0 >= 1 && stage1 >= 1) {  // both GEMM1s issued: free W0's slot
-              tc_commit(BAR(B_WEMPTY + s0));
-              w0_released = true;
-            }
+            if (t) ++stage1; else ++stage0;
           }
+          if (!w0_released && stage0 >= 1 && stage1 >= 1) {  // both GEMM1s issued: free W0's slot
+            if (elect_one()) tc_commit(BAR(B_WEMPTY + s0));
+            __syncwarp();
+            w0_released = true;
+          }
+        }
+        if (elect_one()) {
           tc_commit(BAR(B_WEMPTY + s1));
           if (scaled) tc_commit(BAR(B_WEMPTY + s2));
-          g += scaled ? 3 : 2;
         }
+        __syncwarp();
+        g += scaled ? 3 : 2;
       }
     }
   } else {
