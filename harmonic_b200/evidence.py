@@ -347,9 +347,9 @@ def _allgather(vec, comm):
     t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64))
     if backend == "nccl":
         t = t.cuda()
-    out = torch.empty((world, t.numel()), dtype=torch.float64, device=t.device)
+    out = torch.empty(world * t.numel(), dtype=torch.float64, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)
-    return out.cpu().numpy()
+    return out.view(world, t.numel()).cpu().numpy()
 
 
 # ---------------------------------------------------------------------- harmonic/evidence.py:534-664
