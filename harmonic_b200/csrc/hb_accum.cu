@@ -5,6 +5,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "hb_common.cuh"
@@ -43,7 +44,7 @@ __device__ __forceinline__ void load8<double>(const double* __restrict__ p, long
 }
 
 template <typename PT, typename LT, bool VEC>
-__global__ void __launch_bounds__(ACC_THREADS)
+__global__ void __launch_bounds__(ACC_THREADS, 6)
 accumulate_precomputed_kernel(const PT* __restrict__ lnpred, const LT* __restrict__ lnpost,
                               FoldParams p) {
   __shared__ double scratch[3 * (ACC_THREADS / 32)];
@@ -108,16 +109,28 @@ __global__ void merge_kernel(ChainState* __restrict__ state, double* __restrict_
       state[chain_lo + c] = st;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x < G_N) {
-    const int k = threadIdx.x;
-    double acc = globals[k];
-    for (long long f = 0; f < nflushers; ++f) {
+  // per-call scalars: warp k of block 0 reduces column k of gpart (lane-strided, then a shuffle
+  // tree: a fixed order, so the result is reproducible)
+  if (blockIdx.x == 0 && (threadIdx.x >> 5) < G_N) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc = (k < 2) ? 0.0 : ((k & 1) ? CUDART_INF : -CUDART_INF);
+    for (long long f = lane; f < nflushers; f += 32) {
       const double o = p.gpart[f * G_N + k];
       if (k < 2) acc += o;
       else if (k & 1) acc = fmin(acc, o);
       else acc = fmax(acc, o);
     }
-    globals[k] = acc;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const double v = __shfl_xor_sync(0xffffffffu, acc, o);
+      if (k < 2) acc += v;
+      else if (k & 1) acc = fmin(acc, v);
+      else acc = fmax(acc, v);
+    }
+    if (lane == 0) {
+      const double g = globals[k];
+      globals[k] = (k < 2) ? g + acc : ((k & 1) ? fmin(g, acc) : fmax(g, acc));
+    }
   }
 }
 
@@ -443,6 +456,12 @@ int accumulate_precomputed_device(Accum* acc, const void* lnpred, int pd, const 
 
 using namespace hb;
 
+// Released accumulators are parked here and handed out again for the same (device, nchains):
+// creating one costs several cudaMalloc / stream / event calls, which a per-call Evidence would
+// otherwise pay on every add_chains.
+static std::mutex g_pool_mu;
+static std::vector<Accum*> g_pool;
+
 extern "C" {
 
 int hb_accum_create(int64_t nchains, int device, hb_accum** out) {
@@ -450,6 +469,18 @@ int hb_accum_create(int64_t nchains, int device, hb_accum** out) {
   HB_REQUIRE(nchains >= 1, "nchains must be greater than 0.");
   int rc = require_device(device);
   if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); ++i) {
+      if (g_pool[i]->device == device && g_pool[i]->nchains == nchains) {
+        Accum* a = g_pool[i];
+        g_pool.erase(g_pool.begin() + i);
+        *out = reinterpret_cast<hb_accum*>(a);
+        HB_CUDA(cudaSetDevice(device));
+        return hb_accum_reset(*out);
+      }
+    }
+  }
   Accum* acc = new Accum();
   acc->device = device;
   acc->nchains = nchains;
@@ -472,6 +503,13 @@ int hb_accum_destroy(hb_accum* h) {
   Accum* acc = reinterpret_cast<Accum*>(h);
   cudaSetDevice(acc->device);
   cudaDeviceSynchronize();
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool.size() < 8) {
+      g_pool.push_back(acc);
+      return HB_OK;
+    }
+  }
   cudaFree(acc->state);
   cudaFree(acc->globals);
   cudaFree(acc->start_dev);
@@ -593,20 +631,22 @@ int hb_finalize(hb_accum* h, int shift_mode, double shift_value_in, hb_result* o
   HB_REQUIRE(shift_mode >= HB_MEAN_SHIFT && shift_mode <= HB_ABS_MAX_SHIFT, "unknown shift mode");
   Accum* acc = reinterpret_cast<Accum*>(h);
   HB_CUDA(cudaSetDevice(acc->device));
+  HB_CUDA(cudaDeviceSynchronize());  // accumulate launches may sit on caller streams
   finalize_kernel<<<1, FIN_THREADS>>>(acc->state, acc->globals, acc->nchains, shift_mode,
                                       shift_value_in, acc->fin);
   count_launch();
   HB_CUDA(cudaGetLastError());
-  HB_CUDA(cudaDeviceSynchronize());
-  HB_CUDA(cudaMemcpy(out, acc->fin, sizeof(hb_result), cudaMemcpyDeviceToHost));
   const size_t off = sizeof(hb_result) / sizeof(double);
-  const size_t nb = acc->nchains * sizeof(double);
-  if (ln_inv_per_chain) HB_CUDA(cudaMemcpy(ln_inv_per_chain, acc->fin + off, nb, cudaMemcpyDeviceToHost));
-  if (running_sum) HB_CUDA(cudaMemcpy(running_sum, acc->fin + off + acc->nchains, nb, cudaMemcpyDeviceToHost));
-  if (nsamples_per_chain)
-    HB_CUDA(cudaMemcpy(nsamples_per_chain, acc->fin + off + 2 * acc->nchains, nb, cudaMemcpyDeviceToHost));
-  if (nsamples_eff_per_chain)
-    HB_CUDA(cudaMemcpy(nsamples_eff_per_chain, acc->fin + off + 3 * acc->nchains, nb, cudaMemcpyDeviceToHost));
+  const size_t n = (size_t)acc->nchains;
+  const bool want_arrays = ln_inv_per_chain || running_sum || nsamples_per_chain || nsamples_eff_per_chain;
+  static thread_local std::vector<double> host;
+  host.resize(off + (want_arrays ? 4 * n : 0));
+  HB_CUDA(cudaMemcpy(host.data(), acc->fin, host.size() * sizeof(double), cudaMemcpyDeviceToHost));  // one D2H
+  memcpy(out, host.data(), sizeof(hb_result));
+  if (ln_inv_per_chain) memcpy(ln_inv_per_chain, host.data() + off, n * sizeof(double));
+  if (running_sum) memcpy(running_sum, host.data() + off + n, n * sizeof(double));
+  if (nsamples_per_chain) memcpy(nsamples_per_chain, host.data() + off + 2 * n, n * sizeof(double));
+  if (nsamples_eff_per_chain) memcpy(nsamples_eff_per_chain, host.data() + off + 3 * n, n * sizeof(double));
   return HB_OK;
 }
 

@@ -175,10 +175,55 @@ struct Fold {
     nnan = 0;
   }
 
+  // Whole tile inside the open chain (the common case): no per-row range tests, one rescale of
+  // the running sum per thread and tile, predicated (branch-free) accumulation.
+  template <int R>
+  __device__ __forceinline__ void fold_full(const float (&lnpred)[R], const float (&lnpost)[R]) {
+    float a[R];
+    float lmax = -CUDART_INF_F;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      a[q] = lnpred[q] - lnpost[q];
+      qmax = fmaxf(qmax, lnpred[q]);
+      qmin = fminf(qmin, lnpred[q]);
+      pmax = fmaxf(pmax, lnpost[q]);
+      pmin = fminf(pmin, lnpost[q]);
+      const bool fin = fabsf(a[q]) < CUDART_INF_F;  // false for NaN and +-inf (evidence.py:282-283)
+      const float af = fin ? a[q] : -CUDART_INF_F;
+      lmax = fmaxf(lmax, af);
+      amin = fminf(amin, fin ? a[q] : CUDART_INF_F);
+      gsum += fin ? a[q] : 0.f;
+      gcnt += fin ? 1 : 0;
+      nnan += fin ? 0 : 1;
+      a[q] = af;
+    }
+    amax = fmaxf(amax, lmax);
+    if (lmax > m) {
+      s *= __expf(m - lmax);  // m = -inf, s = 0 at the start: 0 * 0
+      m = lmax;
+    }
+    if (m > -CUDART_INF_F) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) s += __expf(a[q] - m);  // exp(-inf) = 0 for the excluded rows
+    }
+  }
+
   // Feed one tile [t0, t1) of the flusher's rows. Thread owns rows t0 + tid*R + q, q < R.
   template <int R>
   __device__ __forceinline__ void tile(long long t0, long long t1, const float (&lnpred)[R],
                                        const float (&lnpost)[R]) {
+    if (t1 - t0 == (long long)NT * R && t1 <= cur_end) {
+      fold_full<R>(lnpred, lnpost);
+      if (t1 < cur_end) return;
+      // the chain ends exactly at the tile boundary
+      flush();
+      const long long seg_begin = cur_end;
+      do {
+        ++cur_chain;
+        cur_end = (cur_chain < p.nch) ? p.start[cur_chain + 1] : (long long)0x7fffffffffffffffLL;
+      } while (cur_chain < p.nch && cur_end <= seg_begin);
+      return;
+    }
     long long seg_begin = t0;
     const long long r0 = t0 + (long long)tid * R;
     while (true) {

@@ -105,7 +105,17 @@ class Evidence:
     def __del__(self):
         self._release()
 
+    def partials(self):
+        """(nchains, 4) float64 array of this process' per-chain state (m, s, n, n_nan): what is
+        pickled, and what crosses NVLink in the multi-GPU all-gather."""
+        if self._acc is not None:
+            part = np.empty((self.nchains, 4), dtype=np.float64)
+            _lib.check(_lib.load().hb_accum_export(self._acc, part.ctypes.data, None))
+            self._partials = part
+        return self._partials
+
     def __getstate__(self):
+        self.partials()  # pull the device-side streaming state into the picklable image
         st = dict(self.__dict__)
         st["_acc"] = None
         st["_acc_global"] = None
@@ -251,9 +261,6 @@ class Evidence:
         shift_in = float(self.shift_value) if self.shift_set else float("nan")
         _lib.check(lib.hb_finalize(fin, self.shift.value, shift_in, _lib.C.byref(res), per.ctypes.data,
                                    rsum.ctypes.data, npc.ctypes.data, neff.ctypes.data))
-        if comm is None:
-            _lib.check(lib.hb_accum_export(acc, part.ctypes.data, None))
-            self._partials = part
         if not self.shift_set:
             self.set_shift(res.shift_value)
         self._take(res)

@@ -155,7 +155,7 @@ def test_many_tiny_and_empty_chains():
     m = Dummy()
     ev = hm.Evidence(len(lens), m)
     ev.add_lnpred(lnpred, lnpost, start)
-    part = ev._partials
+    part = ev.partials()
     # per-chain logsumexp vs numpy float64 on the float32-rounded inputs
     la = lnpred.astype(np.float32) - lnpost.astype(np.float32)
     for c in rng.integers(0, len(lens), 300):

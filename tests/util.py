@@ -52,13 +52,20 @@ def gaussian_chains(ndim, nchains, nsamples, seed=0, ragged=False):
 
 
 def check_predict(model, x, got, rel=1e-5):
-    """got vs the float64 oracle at the north_star tolerance, widened per sample by 3x the
-    deviation of the float32 restatement (the arithmetic the reference itself runs in) where
-    float32 is ill-conditioned."""
+    """got vs the float64 oracle at the north_star tolerance (1e-5 relative), widened per sample
+    where float32 evaluation is ill-conditioned: by 3x the deviation of the float32 restatement (the
+    arithmetic the reference itself runs in) and by 2x the change of ln phi under +-1 ulp(float32)
+    relative perturbations of the input."""
     want = oracle_predict(model, x, np.float64)
     with np.errstate(all="ignore"):
+        den = np.maximum(np.abs(want), 1.0)
         w32 = oracle_predict(model, x, np.float32).astype(np.float64)
-        slack = 3.0 * np.abs(w32 - want) / np.maximum(np.abs(want), 1.0)
+        slack = 3.0 * np.abs(w32 - want) / den
+        # conditioning: change of ln phi under a one-ulp (float32) relative perturbation of the input
+        x64 = np.asarray(x, dtype=np.float64)
+        for sgn in (1.0, -1.0):
+            wp = oracle_predict(model, x64 * (1.0 + sgn * 2.0**-23), np.float64)
+            slack = slack + 2.0 * np.abs(wp - want) / den
     slack[~np.isfinite(slack)] = 0.0
     return assert_lnphi_close(got, want, rel, slack)
 
