@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libharmonic_b200.so")
 HB_FLOW_REALNVP, HB_FLOW_RQSPLINE = 1, 2
 HB_F32, HB_F64 = 0, 1
 HB_MEM_HOST, HB_MEM_DEVICE = 0, 1
-HB_PATH_AUTO, HB_PATH_SIMT, HB_PATH_TCGEN05 = 0, 1, 2
+HB_PATH_AUTO, HB_PATH_SIMT, HB_PATH_TCGEN05, HB_PATH_SIMT_GENERIC = 0, 1, 2, 3
 HB_ACC_NEW_CALL = 1
 HB_MAX_HIDDEN = 8
 HB_ERR_INVALID, HB_ERR_CUDA, HB_ERR_UNSUPPORTED, HB_ERR_NO_DEVICE = -1, -2, -3, -4

@@ -231,6 +231,7 @@ int hb_flow_destroy(hb_flow* h) {
   if (f->rq_pack) cudaFree(f->rq_pack);
   realnvp_tc_release(f);
   realnvp_simt_release(f);
+  realnvp_small_release(f);
   delete f;
   return HB_OK;
 }
@@ -238,7 +239,10 @@ int hb_flow_destroy(hb_flow* h) {
 int hb_flow_set_path(hb_flow* h, int path) {
   HB_REQUIRE(h != nullptr, "hb_flow_set_path: NULL handle");
   Flow* f = reinterpret_cast<Flow*>(h);
-  HB_REQUIRE(path == HB_PATH_AUTO || path == HB_PATH_SIMT || path == HB_PATH_TCGEN05, "unknown path");
+  HB_REQUIRE(path == HB_PATH_AUTO || path == HB_PATH_SIMT || path == HB_PATH_TCGEN05 ||
+                 path == HB_PATH_SIMT_GENERIC,
+             "unknown path");
+  f->force_generic = path == HB_PATH_SIMT_GENERIC;
   if (path == HB_PATH_TCGEN05 && !f->tc_ok) {
     set_error("tcgen05 path does not support this flow shape");
     return HB_ERR_UNSUPPORTED;

@@ -143,6 +143,148 @@ realnvp_simt_kernel(RealNVPSimtParams P, const XT* __restrict__ x, long long ld,
 }
 
 // ------------------------------------------------------------------------------------------
+// RealNVP, small ndim (2..8): everything in registers, two samples per thread, all layers'
+// weights resident in shared memory as per-hidden-unit records
+//   rec[j] = { b0[j], W0[0..d-1][j], Wt[j][0..u-1], Ws[j][0..u-1] }   (padded to 4 floats)
+// so one warp-uniform LDS.128 stream feeds (d + 2u + 2) FMAs per sample and hidden unit; the
+// hidden activation is never stored.
+// ------------------------------------------------------------------------------------------
+constexpr int SM_THREADS = 128;
+constexpr int SM_R = 2;  // samples per thread
+
+struct SmallParams {
+  const float* pack;   // per layer: 128 records of `rp` floats, then bt[4-padded u], bs[4-padded u]
+  const float* pre;    // pre_offset[D], pre_amp[D] or nullptr
+  int nlayers, nscaled, rp, layer_floats;
+  float T, sum_log_amp;
+  int x_f64, lp_f64;
+};
+
+template <int D, bool FOLD>
+__global__ void __launch_bounds__(SM_THREADS)
+realnvp_small_kernel(SmallParams P, const void* __restrict__ xv, long long ld,
+                     const void* __restrict__ lnpostv, float* __restrict__ lnpred_out, FoldParams fp,
+                     long long nrows, long long rows_per_cta) {
+  constexpr int d = (D == 2) ? 1 : (D == 3) ? 2 : (D == 4) ? 2 : (D == 5) ? 2 : (D == 6) ? 3 : (D == 7) ? 4 : 4;
+  constexpr int u = D - d;
+  constexpr int UP = (u + 3) & ~3;
+  extern __shared__ float wsm[];
+  __shared__ double scratch[3 * (SM_THREADS / 32)];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < P.nlayers * P.layer_floats; i += SM_THREADS) wsm[i] = P.pack[i];
+  __syncthreads();
+  const long long row_lo = (long long)blockIdx.x * rows_per_cta;
+  long long row_hi = row_lo + rows_per_cta;
+  if (row_hi > nrows) row_hi = nrows;
+  const bool had_rows = row_lo < nrows;
+  Fold<SM_THREADS> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
+  const float invT = 1.f / P.T;
+  const float base_const = -(float)D * logf(P.T) - 0.5f * (float)D * 1.8378770664093453f;
+  const int rp = P.rp;
+
+  for (long long t0 = row_lo; t0 < row_hi; t0 += SM_THREADS * SM_R) {
+    float y[SM_R][D];
+    float ldj[SM_R];
+    long long rq[SM_R];
+#pragma unroll
+    for (int q = 0; q < SM_R; ++q) {
+      const long long r = t0 + (long long)tid * SM_R + q;
+      rq[q] = r;
+      const long long rr = (r < row_hi) ? r : row_lo;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float v = P.x_f64 ? (float)static_cast<const double*>(xv)[rr * ld + i]
+                          : static_cast<const float*>(xv)[rr * ld + i];
+        if (P.pre) v = (v - P.pre[i]) / P.pre[D + i];
+        y[q][i] = v;
+      }
+      ldj[q] = 0.f;
+    }
+    for (int l = 0; l < P.nlayers; ++l) {
+      const float* L = wsm + (size_t)l * P.layer_floats;
+      const bool scaled = l < P.nscaled;
+      float sh[SM_R][u], sc[SM_R][u];
+#pragma unroll
+      for (int q = 0; q < SM_R; ++q)
+#pragma unroll
+        for (int k = 0; k < u; ++k) {
+          sh[q][k] = L[128 * rp + k];
+          sc[q][k] = L[128 * rp + UP + k];
+        }
+#pragma unroll 4
+      for (int j = 0; j < 128; ++j) {
+        const float* rec = L + j * rp;
+        float w[1 + d + 2 * u];
+#pragma unroll
+        for (int i = 0; i < 1 + d + 2 * u; i += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(rec + i);
+          w[i] = t4.x;
+          if (i + 1 < 1 + d + 2 * u) w[i + 1] = t4.y;
+          if (i + 2 < 1 + d + 2 * u) w[i + 2] = t4.z;
+          if (i + 3 < 1 + d + 2 * u) w[i + 3] = t4.w;
+        }
+#pragma unroll
+        for (int q = 0; q < SM_R; ++q) {
+          float h = w[0];
+#pragma unroll
+          for (int i = 0; i < d; ++i) h = fmaf(y[q][i], w[1 + i], h);
+          h = fmaxf(h, 0.01f * h);
+#pragma unroll
+          for (int k = 0; k < u; ++k) {
+            sh[q][k] = fmaf(h, w[1 + d + k], sh[q][k]);
+            sc[q][k] = fmaf(h, w[1 + d + u + k], sc[q][k]);  // zero weights for unscaled layers
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < SM_R; ++q) {
+#pragma unroll
+        for (int k = 0; k < u; ++k) {
+          float y1 = y[q][d + k] - sh[q][k];
+          if (scaled) {
+            float s = softplus_acc(sc[q][k]);
+            s = fminf(fmaxf(s, 1e-3f), 1e3f);
+            s = (sc[q][k] != sc[q][k]) ? sc[q][k] : s;
+            y1 = y1 / s;
+            ldj[q] -= logf(s);
+          }
+          y[q][d + k] = y1;
+        }
+        if (l + 1 < P.nlayers) {  // inverse permute: rotate left by one
+          const float y0 = y[q][0];
+#pragma unroll
+          for (int i = 0; i < D - 1; ++i) y[q][i] = y[q][i + 1];
+          y[q][D - 1] = y0;
+        }
+      }
+    }
+    float a[SM_R], b[SM_R];
+#pragma unroll
+    for (int q = 0; q < SM_R; ++q) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const float z = y[q][i] * invT;
+        ss = fmaf(z, z, ss);
+      }
+      a[q] = -0.5f * ss + base_const + ldj[q] - P.sum_log_amp;
+      const bool live = rq[q] < row_hi;
+      if (live && lnpred_out) lnpred_out[rq[q]] = a[q];
+      b[q] = 0.f;
+      if (FOLD && live)
+        b[q] = P.lp_f64 ? (float)static_cast<const double*>(lnpostv)[rq[q]]
+                        : static_cast<const float*>(lnpostv)[rq[q]];
+    }
+    if (FOLD) {
+      long long t1 = t0 + SM_THREADS * SM_R;
+      if (t1 > row_hi) t1 = row_hi;
+      fold.tile<SM_R>(t0, t1, a, b);
+    }
+  }
+  if (FOLD) fold.finish(had_rows);
+}
+
+// ------------------------------------------------------------------------------------------
 // RQSpline, any ndim / hidden sizes.  Packed weights per flow layer i:
 //   MLP dense m = 0..nmlp-2 (each followed by tanh): W[in][outpad], b[outpad]
 //   per transformed feature j: fused (last MLP dense) x (output dense rows of j):
@@ -437,11 +579,141 @@ static void plan_grid(int device, long long n, size_t smem, long long* nfl, long
   *rpc = r;
 }
 
+// ---- small-ndim register path ------------------------------------------------------------------
+struct SmallCache {
+  float* dev = nullptr;
+  SmallParams P;
+};
+
+static int realnvp_small_prepare(Flow* f, SmallParams* P) {
+  if (f->small_cache) {
+    *P = static_cast<SmallCache*>(f->small_cache)->P;
+    return HB_OK;
+  }
+  const int d = f->d, u = f->u, nl = f->nlayers;
+  const int rp = (1 + d + 2 * u + 3) & ~3;
+  const int up = (u + 3) & ~3;
+  const int layer_floats = 128 * rp + 2 * up;
+  std::vector<float> pack((size_t)nl * layer_floats, 0.f);
+  const float* w = f->host_weights.data();
+  for (int l = 0; l < nl; ++l) {
+    const bool scaled = l < f->desc.n_scaled;
+    const float* W0 = w + f->layer_off[l];
+    const float* b0 = W0 + (size_t)d * 128;
+    const float* Wt = b0 + 128;
+    const float* bt = Wt + (size_t)128 * u;
+    const float* Ws = bt + u;
+    const float* bs = Ws + (size_t)128 * u;
+    float* L = pack.data() + (size_t)l * layer_floats;
+    for (int j = 0; j < 128; ++j) {
+      float* rec = L + (size_t)j * rp;
+      rec[0] = b0[j];
+      for (int i = 0; i < d; ++i) rec[1 + i] = W0[(size_t)i * 128 + j];
+      for (int k = 0; k < u; ++k) rec[1 + d + k] = Wt[(size_t)j * u + k];
+      if (scaled)
+        for (int k = 0; k < u; ++k) rec[1 + d + u + k] = Ws[(size_t)j * u + k];
+    }
+    for (int k = 0; k < u; ++k) L[128 * rp + k] = bt[k];
+    if (scaled)
+      for (int k = 0; k < u; ++k) L[128 * rp + up + k] = bs[k];
+  }
+  SmallCache* c = new SmallCache();
+  HB_CUDA(cudaMalloc(&c->dev, pack.size() * sizeof(float)));
+  HB_CUDA(cudaMemcpy(c->dev, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
+  c->P.pack = c->dev;
+  c->P.pre = f->desc.standardize ? f->dev_weights : nullptr;
+  c->P.nlayers = nl;
+  c->P.nscaled = f->desc.n_scaled;
+  c->P.rp = rp;
+  c->P.layer_floats = layer_floats;
+  c->P.sum_log_amp = f->sum_log_amp;
+  f->small_cache = c;
+  *P = c->P;
+  return HB_OK;
+}
+
+void realnvp_small_release(Flow* f) {
+  if (!f->small_cache) return;
+  SmallCache* c = static_cast<SmallCache*>(f->small_cache);
+  if (c->dev) cudaFree(c->dev);
+  delete c;
+  f->small_cache = nullptr;
+}
+
+template <int D>
+static int small_launch(const SmallParams& P, bool fold, int grid, size_t smem, const void* x, long long ld,
+                        const void* lnpost, float* lnpred_out, const FoldParams& fp, long long n,
+                        long long rpc, cudaStream_t st) {
+  if (fold) {
+    auto k = realnvp_small_kernel<D, true>;
+    HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, SM_THREADS, smem, st>>>(P, x, ld, lnpost, lnpred_out, fp, n, rpc);
+  } else {
+    auto k = realnvp_small_kernel<D, false>;
+    HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, SM_THREADS, smem, st>>>(P, x, ld, lnpost, lnpred_out, fp, n, rpc);
+  }
+  return HB_OK;
+}
+
+// returns HB_ERR_UNSUPPORTED (without setting an error) when the shape does not fit this path
+static int realnvp_small_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                             const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                             const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                             long long b, cudaStream_t st) {
+  const int D = f->desc.ndim;
+  if (D < 2 || D > 8) return HB_ERR_UNSUPPORTED;
+  SmallParams P;
+  int rc = realnvp_small_prepare(f, &P);
+  if (rc) return rc;
+  const size_t smem = (size_t)P.nlayers * P.layer_floats * sizeof(float);
+  if (smem > 200 * 1024) return HB_ERR_UNSUPPORTED;
+  P.T = T;
+  P.x_f64 = x_dtype == HB_F64;
+  P.lp_f64 = lp_dtype == HB_F64;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+  int per_sm = (int)((227 * 1024) / (smem + 2048));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  const long long tile = SM_THREADS * SM_R;
+  long long nfl = (long long)sms * per_sm;
+  long long rpc = (n + nfl - 1) / nfl;
+  rpc = ((rpc + tile - 1) / tile) * tile;
+  nfl = (n + rpc - 1) / rpc;
+  FoldParams fp{};
+  if (acc) {
+    rc = prepare_fold(acc, start, chain_lo, chain_hi, a, b, nfl, rpc, &fp, st);
+    if (rc) return rc;
+  }
+  timing_begin(st);
+  switch (D) {
+    case 2: rc = small_launch<2>(P, acc != nullptr, (int)nfl, smem, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 3: rc = small_launch<3>(P, acc != nullptr, (int)nfl, smem, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 4: rc = small_launch<4>(P, acc != nullptr, (int)nfl, smem, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 5: rc = small_launch<5>(P, acc != nullptr, (int)nfl, smem, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 6: rc = small_launch<6>(P, acc != nullptr, (int)nfl, smem, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 7: rc = small_launch<7>(P, acc != nullptr, (int)nfl, smem, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    default: rc = small_launch<8>(P, acc != nullptr, (int)nfl, smem, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+  }
+  timing_end(st);
+  if (rc) return rc;
+  count_launch();
+  HB_CUDA(cudaGetLastError());
+  if (acc) return launch_merge(acc, fp, chain_lo, nfl, st);
+  return HB_OK;
+}
+
 int realnvp_simt_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
                      const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
                      const int64_t* start, long long chain_lo, long long chain_hi, long long a,
                      long long b, cudaStream_t st) {
   if (n <= 0) return HB_OK;
+  if (!f->force_generic) {
+    const int rs = realnvp_small_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start,
+                                     chain_lo, chain_hi, a, b, st);
+    if (rs != HB_ERR_UNSUPPORTED) return rs;
+  }
   RealNVPSimtParams P;
   int rc = realnvp_simt_prepare(f, &P);
   if (rc) return rc;

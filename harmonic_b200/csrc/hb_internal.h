@@ -48,6 +48,8 @@ struct Flow {
   std::vector<size_t> rq_off;
   size_t rq_pack_floats = 0;
   void* simt_params = nullptr;  // cached RealNVPSimtParams (hb_flow_simt.cu)
+  void* small_cache = nullptr;  // cached small-ndim register-path weights (hb_flow_simt.cu)
+  bool force_generic = false;   // HB_PATH_SIMT_GENERIC: skip the small-ndim register path
   // tcgen05 image (hi/lo split, UMMA canonical layout, see hb_realnvp_tc.cu)
   void* tc_image = nullptr;
   size_t tc_image_bytes = 0;
@@ -72,5 +74,6 @@ int realnvp_tc_prepare(Flow* f);  // builds tc_image; sets tc_ok
 int rqspline_prepare(Flow* f);
 void realnvp_tc_release(Flow* f);
 void realnvp_simt_release(Flow* f);
+void realnvp_small_release(Flow* f);
 
 }  // namespace hb

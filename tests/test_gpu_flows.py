@@ -16,11 +16,16 @@ def samples(n, ndim, seed=0, scale=1.0):
     return np.random.default_rng(seed).standard_normal((n, ndim)) * scale
 
 
-@pytest.mark.parametrize("ndim", [2, 3, 5, 8, 17, 64])
+@pytest.mark.parametrize("ndim", [2, 3, 4, 5, 6, 7, 8, 17, 64])
 @pytest.mark.parametrize("standardize", [False, True])
-def test_realnvp_predict_simt(ndim, standardize):
+@pytest.mark.parametrize("path", [_lib.HB_PATH_SIMT, _lib.HB_PATH_SIMT_GENERIC])
+def test_realnvp_predict_simt(ndim, standardize, path):
+    """HB_PATH_SIMT uses the register kernel for ndim <= 8 and the generic kernel above;
+    HB_PATH_SIMT_GENERIC forces the generic (shared-memory) kernel."""
+    if path == _lib.HB_PATH_SIMT_GENERIC and ndim > 8:
+        pytest.skip("same kernel as HB_PATH_SIMT")
     m = util.make_realnvp(ndim, seed=ndim, standardize=standardize, temperature=0.8)
-    m.kernel_path = _lib.HB_PATH_SIMT
+    m.kernel_path = path
     x = samples(1000, ndim, seed=1, scale=1.5)
     got = m.predict(x)
     assert got.dtype == np.float32 and got.shape == (1000,)
