@@ -347,15 +347,24 @@ def main():
                 "frac": (ach / peak) if ach else None, "traffic": None,
                 "kernel": "accumulate_precomputed_kernel", "kernel_ms": kms,
                 "peak_source": "HBM copy bandwidth, of %s" % peak_kind}
-    else:
+    elif name == "cfg4" and args.path != "simt":
         ach = wl.FLOP_PER_SAMPLE[name] * n_local / (kms * 1e-3) / 1e12 if kms else None
         peak = float(peaks["bf16_tflops"]) / 2.0
-        tc = name == "cfg4" and args.path != "simt"
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None, "traffic": None,
-                "kernel": "realnvp_tc_kernel" if tc else "simt flow kernel", "kernel_ms": kms,
+                "kernel": "realnvp_tc_kernel", "kernel_ms": kms,
                 "peak_source": "TF32 dense = bf16 burst / 2, of %s" % peak_kind,
-                "issued_mma_flop_factor": 3.0 if tc else None,
+                "issued_mma_flop_factor": 3.0, "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
+    else:
+        # small-ndim flows run on the FP32 CUDA cores (tensor tiles would be >= 75 % padding):
+        # denominator = 148 SMs x 128 FMA lanes x 2 FLOP x max SM clock (nominal, not measured)
+        ach = wl.FLOP_PER_SAMPLE[name] * n_local / (kms * 1e-3) / 1e12 if kms else None
+        peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        roof = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": (ach / peak) if ach else None, "traffic": None,
+                "kernel": {"cfg2": "rqspline_fast_kernel", "cfg3": "realnvp_small_kernel",
+                           "cfg1": "realnvp_small_kernel"}.get(name, "simt flow kernel"), "kernel_ms": kms,
+                "peak_source": "FP32 CUDA-core FMA peak at the max SM clock (nominal)",
                 "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
 
     cpu = None

@@ -35,7 +35,7 @@ def make_model(name):
     if name == "cfg1":
         return util.make_realnvp(5, 2, 4, seed=1, standardize=True, temperature=0.8, ws=0.3)
     if name == "cfg2":
-        return util.make_rqspline(2, 8, 8, (64, 64), seed=2, standardize=False, temperature=0.9, ws=0.5)
+        return util.make_rqspline(2, 8, 8, (64, 64), seed=2, standardize=False, temperature=0.9, ws=0.15)
     raise ValueError(name)
 
 

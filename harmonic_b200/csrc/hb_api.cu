@@ -229,6 +229,7 @@ int hb_flow_destroy(hb_flow* h) {
   cudaDeviceSynchronize();
   if (f->dev_weights) cudaFree(f->dev_weights);
   if (f->rq_pack) cudaFree(f->rq_pack);
+  if (f->rqf_pack) cudaFree(f->rqf_pack);
   realnvp_tc_release(f);
   realnvp_simt_release(f);
   realnvp_small_release(f);

@@ -468,6 +468,260 @@ rqspline_simt_kernel(RQParams P, const XT* __restrict__ x, long long ld,
 }
 
 // ------------------------------------------------------------------------------------------
+// RQSpline fast path: n_hidden == 2, ndim 2..8, 8 bins.  Everything in registers, two samples per
+// thread; weights are read through the read-only path with warp-uniform float4 loads.  Per flow
+// layer:  a1 = tanh(Dense_0(where(mask, y, 0)))            (ndim values)
+//         for every transformed feature f:  P_f = c_f + sum_j tanh(Dense_1(a1))_j * M_f[j][:]
+//         (M_f = last MLP Dense x output Dense rows of f, pre-multiplied on the host; the hidden
+//         activation is recomputed per feature instead of being stored)
+//         spline forward on feature f, then the scalar affine on all features.
+// Packed per layer: W1[D][D4] b1[D4] | W2T[h1][D4 + 4] (row j: W2[0..D-1][j], b2[j]) |
+//                   per transformed feature: M[h1][28], c[28] | scales[D4] shifts[D4]
+// ------------------------------------------------------------------------------------------
+constexpr int RQF_THREADS = 128;
+constexpr int RQF_R = 2;
+constexpr int RQF_NP = 28;  // 3*8+1 = 25 spline parameters padded to 28
+
+struct RQFastParams {
+  const float* pack;
+  const float* pre;
+  int nlayers, h1, layer_floats_even, layer_floats_odd;  // layers alternate parity -> sizes differ
+  float lo, hi, T, sum_log_amp;
+  int x_f64, lp_f64;
+};
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  // |x| < 0.25: odd series (rel. err < 2e-7); else 1 - 2 / (exp(2x) + 1) with MUFU ex2 / rcp
+  const float x2 = x * x;
+  const float ser = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.13333334f), -0.33333334f), 1.0f);
+  const float e = exp2f(2.8853900817779268f * fabsf(x));  // exp(2|x|)
+  const float big = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+  return (fabsf(x) < 0.25f) ? ser : big;
+}
+
+// distrax RationalQuadraticSpline forward, K = 8, parameters in registers (static indexing only)
+__device__ __forceinline__ void rqs_forward_reg(float x, const float (&p)[RQF_NP], float lo, float hi,
+                                                float& yout, float& ldout) {
+  constexpr int K = 8;
+  const float mbs = 1e-4f, mks = 1e-4f;
+  const float off = 0.5411666523385311f;  // log(exp(1 - 1e-4) - 1)
+  const float span = (hi - lo) - (float)K * mbs;
+  float mw = p[0], mh = p[K];
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    mw = fmaxf(mw, p[k]);
+    mh = fmaxf(mh, p[K + k]);
+  }
+  float ew[K], eh[K], sw = 0.f, shh = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ew[k] = __expf(p[k] - mw);
+    eh[k] = __expf(p[K + k] - mh);
+    sw += ew[k];
+    shh += eh[k];
+  }
+  const float iw = span / sw, ih = span / shh;
+  float xl = lo, yl = lo, cw = 0.f, chh = 0.f;
+  float bxl = lo, bxr = lo, byl = lo, byr = lo, sl_raw = p[2 * K], sr_raw = p[2 * K + 1];
+  bool found = false;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    cw += fmaf(ew[k], iw, mbs);
+    chh += fmaf(eh[k], ih, mbs);
+    const float xr = (k == K - 1) ? hi : lo + cw;
+    const float yr = (k == K - 1) ? hi : lo + chh;
+    const bool in = (!found) && (x >= xl) && (x < xr);
+    if (k == 0 || in) {  // bin 0 is the default (e.g. NaN input)
+      bxl = xl; bxr = xr; byl = yl; byr = yr;
+      sl_raw = p[2 * K + k];
+      sr_raw = p[2 * K + k + 1];
+    }
+    found = found || in;
+    xl = xr;
+    yl = yr;
+  }
+  const bool below = x <= lo, above = x >= hi;
+  if (below) { sl_raw = p[2 * K]; }
+  if (above) { sl_raw = p[3 * K]; }
+  const float sl = softplus_acc(sl_raw + off) + mks;
+  const float sr = softplus_acc(sr_raw + off) + mks;
+  const float bw = bxr - bxl, bh = byr - byl;
+  const float delta = bh / bw;
+  float z = (x - bxl) / bw;
+  z = fminf(fmaxf(z, 0.f), 1.f);
+  if (x != x) z = x;  // jnp.clip propagates NaN
+  const float sq_z = z * z;
+  const float z1mz = z - sq_z;
+  const float omz = 1.f - z;
+  const float slopes_term = sr + sl - 2.f * delta;
+  const float numerator = bh * (delta * sq_z + sl * z1mz);
+  const float denominator = delta + slopes_term * z1mz;
+  float yv = byl + numerator / denominator;
+  float ldv = 2.f * __logf(delta) + __logf(sr * sq_z + 2.f * delta * z1mz + sl * omz * omz) -
+              2.f * __logf(denominator);
+  if (below) { yv = (x - lo) * sl + lo; ldv = __logf(sl); }
+  if (above) { yv = (x - hi) * sl + hi; ldv = __logf(sl); }
+  yout = yv;
+  ldout = ldv;
+}
+
+template <int D, bool FOLD>
+__global__ void __launch_bounds__(RQF_THREADS)
+rqspline_fast_kernel(RQFastParams P, const void* __restrict__ xv, long long ld,
+                     const void* __restrict__ lnpostv, float* __restrict__ lnpred_out, FoldParams fp,
+                     long long nrows, long long rows_per_cta) {
+  constexpr int D4 = (D + 3) & ~3;
+  __shared__ double scratch[3 * (RQF_THREADS / 32)];
+  const int tid = threadIdx.x;
+  const long long row_lo = (long long)blockIdx.x * rows_per_cta;
+  long long row_hi = row_lo + rows_per_cta;
+  if (row_hi > nrows) row_hi = nrows;
+  const bool had_rows = row_lo < nrows;
+  Fold<RQF_THREADS> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
+  const float base_const = -0.5f * (float)D * 1.8378770664093453f - 0.5f * (float)D * logf(P.T);
+  const float invT = 1.f / P.T;
+  const int h1 = P.h1;
+
+  for (long long t0 = row_lo; t0 < row_hi; t0 += RQF_THREADS * RQF_R) {
+    float y[RQF_R][D], ldet[RQF_R];
+    long long rq[RQF_R];
+#pragma unroll
+    for (int q = 0; q < RQF_R; ++q) {
+      const long long r = t0 + (long long)tid * RQF_R + q;
+      rq[q] = r;
+      const long long rr = (r < row_hi) ? r : row_lo;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float v = P.x_f64 ? (float)static_cast<const double*>(xv)[rr * ld + i]
+                          : static_cast<const float*>(xv)[rr * ld + i];
+        if (P.pre) v = (v - P.pre[i]) / P.pre[D + i];
+        y[q][i] = v;
+      }
+      ldet[q] = 0.f;
+    }
+    for (int li = P.nlayers - 1; li >= 0; --li) {  // Inverse(Chain).inverse: last layer first
+      const int par = li & 1;  // mask = (j % 2 == 1) for even layers, negated for odd; True = pass-through
+      // offset of layer li: even layers first have size fe, odd fo; layers are stored in order
+      const size_t loff = (size_t)((li + 1) >> 1) * P.layer_floats_even + (size_t)(li >> 1) * P.layer_floats_odd;
+      const float* L = P.pack + loff;
+      const float* W1 = L;                  // [D][D4]
+      const float* b1 = W1 + D * D4;        // [D4]
+      const float* W2T = b1 + D4;           // [h1][D4 + 4]
+      const float* feat = W2T + (size_t)h1 * (D4 + 4);
+      // ---- a1 = tanh(Dense_0(where(mask, y, 0)))
+      float a1[RQF_R][D];
+#pragma unroll
+      for (int q = 0; q < RQF_R; ++q)
+#pragma unroll
+        for (int o = 0; o < D; ++o) a1[q][o] = __ldg(b1 + o);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const bool vis = ((i & 1) == 1) != (par == 1);
+        if (!vis) continue;  // compile-time per (i, par) after unrolling both parities below
+#pragma unroll
+        for (int o = 0; o < D; ++o) {
+          const float w = __ldg(W1 + i * D4 + o);
+#pragma unroll
+          for (int q = 0; q < RQF_R; ++q) a1[q][o] = fmaf(y[q][i], w, a1[q][o]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RQF_R; ++q)
+#pragma unroll
+        for (int o = 0; o < D; ++o) a1[q][o] = tanh_fast(a1[q][o]);
+      // ---- every transformed feature
+      int blk = 0;
+      const size_t blk_floats = (size_t)h1 * RQF_NP + RQF_NP;
+#pragma unroll
+      for (int f = 0; f < D; ++f) {
+        const bool vis = ((f & 1) == 1) != (par == 1);
+        if (vis) continue;
+        const float* M = feat + (size_t)blk * blk_floats;
+        const float* cb = M + (size_t)h1 * RQF_NP;
+        float out[RQF_R][RQF_NP];
+#pragma unroll
+        for (int p4 = 0; p4 < RQF_NP; p4 += 4) {
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb + p4));
+#pragma unroll
+          for (int q = 0; q < RQF_R; ++q) {
+            out[q][p4] = c4.x; out[q][p4 + 1] = c4.y; out[q][p4 + 2] = c4.z; out[q][p4 + 3] = c4.w;
+          }
+        }
+#pragma unroll 2
+        for (int j = 0; j < h1; ++j) {
+          float w2[D4 + 4];
+#pragma unroll
+          for (int i4 = 0; i4 < D4 + 4; i4 += 4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(W2T + (size_t)j * (D4 + 4) + i4));
+            w2[i4] = t4.x; w2[i4 + 1] = t4.y; w2[i4 + 2] = t4.z; w2[i4 + 3] = t4.w;
+          }
+          float a2[RQF_R];
+#pragma unroll
+          for (int q = 0; q < RQF_R; ++q) {
+            float h = w2[D4];  // b2[j]
+#pragma unroll
+            for (int i = 0; i < D; ++i) h = fmaf(a1[q][i], w2[i], h);
+            a2[q] = tanh_fast(h);
+          }
+#pragma unroll
+          for (int p4 = 0; p4 < RQF_NP; p4 += 4) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(M + (size_t)j * RQF_NP + p4));
+#pragma unroll
+            for (int q = 0; q < RQF_R; ++q) {
+              out[q][p4] = fmaf(a2[q], m4.x, out[q][p4]);
+              out[q][p4 + 1] = fmaf(a2[q], m4.y, out[q][p4 + 1]);
+              out[q][p4 + 2] = fmaf(a2[q], m4.z, out[q][p4 + 2]);
+              out[q][p4 + 3] = fmaf(a2[q], m4.w, out[q][p4 + 3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < RQF_R; ++q) {
+          float yo, lo_;
+          rqs_forward_reg(y[q][f], out[q], P.lo, P.hi, yo, lo_);
+          y[q][f] = yo;
+          ldet[q] += lo_;
+        }
+        ++blk;
+      }
+      // ---- scalar affine, all dims
+      const float* sc = feat + (size_t)blk * blk_floats;
+      const float* sh = sc + D4;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const float s = __ldg(sc + i), t = __ldg(sh + i);
+        const float ls = __logf(fabsf(s));
+#pragma unroll
+        for (int q = 0; q < RQF_R; ++q) {
+          y[q][i] = fmaf(y[q][i], s, t);
+          ldet[q] += ls;
+        }
+      }
+    }
+    float a[RQF_R], b[RQF_R];
+#pragma unroll
+    for (int q = 0; q < RQF_R; ++q) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < D; ++i) ss = fmaf(y[q][i], y[q][i], ss);
+      a[q] = -0.5f * ss * invT + base_const + ldet[q] - P.sum_log_amp;
+      const bool live = rq[q] < row_hi;
+      if (live && lnpred_out) lnpred_out[rq[q]] = a[q];
+      b[q] = 0.f;
+      if (FOLD && live)
+        b[q] = P.lp_f64 ? (float)static_cast<const double*>(lnpostv)[rq[q]]
+                        : static_cast<const float*>(lnpostv)[rq[q]];
+    }
+    if (FOLD) {
+      long long t1 = t0 + RQF_THREADS * RQF_R;
+      if (t1 > row_hi) t1 = row_hi;
+      fold.tile<RQF_R>(t0, t1, a, b);
+    }
+  }
+  if (FOLD) fold.finish(had_rows);
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static inline int pad8(int n) { return (n + 7) & ~7; }
@@ -749,6 +1003,129 @@ int realnvp_simt_run(Flow* f, float T, const void* x, int x_dtype, long long ld,
   return HB_OK;
 }
 
+
+// ---- RQSpline fast path packing ---------------------------------------------------------------
+static bool rqspline_fast_eligible(const hb_flow_desc& ds) {
+  return ds.n_hidden == 2 && ds.ndim >= 2 && ds.ndim <= 8 && ds.n_bins == 8 && ds.hidden[0] >= 1;
+}
+
+static int rqspline_fast_prepare(Flow* f) {
+  const hb_flow_desc& ds = f->desc;
+  if (!rqspline_fast_eligible(ds)) return HB_OK;
+  const int D = ds.ndim, K = ds.n_bins, npar = 3 * K + 1, D4 = (D + 3) & ~3;
+  const int h1 = ds.hidden[0], h2 = ds.hidden[1];
+  std::vector<float> pack;
+  const float* w = f->host_weights.data() + 2 * (size_t)D;
+  size_t fe = 0, fo = 0;
+  for (int i = 0; i < ds.n_layers; ++i) {
+    const size_t begin = pack.size();
+    const float* W1 = w; w += (size_t)D * D;
+    const float* b1 = w; w += D;
+    const float* W2 = w; w += (size_t)D * h1;
+    const float* b2 = w; w += h1;
+    const float* W3 = w; w += (size_t)h1 * h2;
+    const float* b3 = w; w += h2;
+    const float* Wout = w; w += (size_t)h2 * D * npar;
+    const float* bout = w; w += (size_t)D * npar;
+    const float* scales = w; w += D;
+    const float* shifts = w; w += D;
+    for (int r = 0; r < D; ++r)
+      for (int c = 0; c < D4; ++c) pack.push_back(c < D ? W1[(size_t)r * D + c] : 0.f);
+    for (int c = 0; c < D4; ++c) pack.push_back(c < D ? b1[c] : 0.f);
+    for (int j = 0; j < h1; ++j) {
+      for (int c = 0; c < D4; ++c) pack.push_back(c < D ? W2[(size_t)c * h1 + j] : 0.f);
+      pack.push_back(b2[j]);
+      pack.push_back(0.f); pack.push_back(0.f); pack.push_back(0.f);
+    }
+    const int par = i & 1;
+    for (int j = 0; j < D; ++j) {
+      const bool visible = ((j & 1) == 1) != (par == 1);
+      if (visible) continue;
+      for (int r = 0; r < h1; ++r)
+        for (int c = 0; c < RQF_NP; ++c) {
+          double acc = 0.0;
+          if (c < npar)
+            for (int q = 0; q < h2; ++q)
+              acc += (double)W3[(size_t)r * h2 + q] * (double)Wout[(size_t)q * D * npar + (size_t)j * npar + c];
+          pack.push_back((float)acc);
+        }
+      for (int c = 0; c < RQF_NP; ++c) {
+        double acc = 0.0;
+        if (c < npar) {
+          acc = bout[(size_t)j * npar + c];
+          for (int q = 0; q < h2; ++q) acc += (double)b3[q] * (double)Wout[(size_t)q * D * npar + (size_t)j * npar + c];
+        }
+        pack.push_back((float)acc);
+      }
+    }
+    for (int c = 0; c < D4; ++c) pack.push_back(c < D ? scales[c] : 1.f);
+    for (int c = 0; c < D4; ++c) pack.push_back(c < D ? shifts[c] : 0.f);
+    if (par == 0) fe = pack.size() - begin; else fo = pack.size() - begin;
+  }
+  HB_CUDA(cudaMalloc(&f->rqf_pack, pack.size() * sizeof(float)));
+  HB_CUDA(cudaMemcpy(f->rqf_pack, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
+  f->rqf_fe = (int)fe;
+  f->rqf_fo = (int)(fo ? fo : fe);
+  return HB_OK;
+}
+
+template <int D>
+static int rqf_launch(const RQFastParams& P, bool fold, int grid, const void* x, long long ld,
+                      const void* lnpost, float* lnpred_out, const FoldParams& fp, long long n,
+                      long long rpc, cudaStream_t st) {
+  if (fold) rqspline_fast_kernel<D, true><<<grid, RQF_THREADS, 0, st>>>(P, x, ld, lnpost, lnpred_out, fp, n, rpc);
+  else rqspline_fast_kernel<D, false><<<grid, RQF_THREADS, 0, st>>>(P, x, ld, lnpost, lnpred_out, fp, n, rpc);
+  return HB_OK;
+}
+
+static int rqspline_fast_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                             const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                             const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                             long long b, cudaStream_t st) {
+  const hb_flow_desc& ds = f->desc;
+  RQFastParams P;
+  P.pack = f->rqf_pack;
+  P.pre = ds.standardize ? f->dev_weights : nullptr;
+  P.nlayers = ds.n_layers;
+  P.h1 = ds.hidden[0];
+  P.layer_floats_even = f->rqf_fe;
+  P.layer_floats_odd = f->rqf_fo;
+  P.lo = ds.range_min;
+  P.hi = ds.range_max;
+  P.T = T;
+  P.sum_log_amp = f->sum_log_amp;
+  P.x_f64 = x_dtype == HB_F64;
+  P.lp_f64 = lp_dtype == HB_F64;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+  const long long tile = RQF_THREADS * RQF_R;
+  long long nfl = (long long)sms * 8;
+  long long rpc = (n + nfl - 1) / nfl;
+  rpc = ((rpc + tile - 1) / tile) * tile;
+  nfl = (n + rpc - 1) / rpc;
+  FoldParams fp{};
+  int rc;
+  if (acc) {
+    rc = prepare_fold(acc, start, chain_lo, chain_hi, a, b, nfl, rpc, &fp, st);
+    if (rc) return rc;
+  }
+  timing_begin(st);
+  switch (ds.ndim) {
+    case 2: rqf_launch<2>(P, acc != nullptr, (int)nfl, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 3: rqf_launch<3>(P, acc != nullptr, (int)nfl, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 4: rqf_launch<4>(P, acc != nullptr, (int)nfl, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 5: rqf_launch<5>(P, acc != nullptr, (int)nfl, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 6: rqf_launch<6>(P, acc != nullptr, (int)nfl, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    case 7: rqf_launch<7>(P, acc != nullptr, (int)nfl, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+    default: rqf_launch<8>(P, acc != nullptr, (int)nfl, x, ld, lnpost, lnpred_out, fp, n, rpc, st); break;
+  }
+  timing_end(st);
+  count_launch();
+  HB_CUDA(cudaGetLastError());
+  if (acc) return launch_merge(acc, fp, chain_lo, nfl, st);
+  return HB_OK;
+}
+
 // ---- RQSpline packing ---------------------------------------------------------------------
 int rqspline_prepare(Flow* f) {
   const hb_flow_desc& ds = f->desc;
@@ -834,7 +1211,7 @@ int rqspline_prepare(Flow* f) {
   HB_CUDA(cudaMemcpy(f->rq_pack, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
   f->rq_pack_floats = pack.size();
   f->rq_off.assign(1, lay_off);
-  return HB_OK;
+  return rqspline_fast_prepare(f);
 }
 
 int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
@@ -842,6 +1219,9 @@ int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, lon
                  const int64_t* start, long long chain_lo, long long chain_hi, long long a,
                  long long b, cudaStream_t st) {
   if (n <= 0) return HB_OK;
+  if (f->rqf_pack && !f->force_generic)
+    return rqspline_fast_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start, chain_lo,
+                             chain_hi, a, b, st);
   const hb_flow_desc& ds = f->desc;
   RQParams P;
   P.pack = f->rq_pack;

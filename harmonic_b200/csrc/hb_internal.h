@@ -48,6 +48,8 @@ struct Flow {
   std::vector<size_t> rq_off;
   size_t rq_pack_floats = 0;
   void* simt_params = nullptr;  // cached RealNVPSimtParams (hb_flow_simt.cu)
+  float* rqf_pack = nullptr;    // RQSpline fast-path weights (hb_flow_simt.cu)
+  int rqf_fe = 0, rqf_fo = 0;   // floats per even / odd flow layer in rqf_pack
   void* small_cache = nullptr;  // cached small-ndim register-path weights (hb_flow_simt.cu)
   bool force_generic = false;   // HB_PATH_SIMT_GENERIC: skip the small-ndim register path
   // tcgen05 image (hi/lo split, UMMA canonical layout, see hb_realnvp_tc.cu)

@@ -53,10 +53,18 @@ def test_realnvp_layer_counts_and_temperature(layers):
 
 
 @pytest.mark.parametrize("ndim,hidden,layers", [(2, (32, 32), 3), (2, (64, 64), 8), (4, (64, 64), 8),
-                                                 (5, (16,), 2), (7, (8, 24, 16), 3), (3, (), 2)])
+                                                 (5, (16,), 2), (7, (8, 24, 16), 3), (3, (), 2),
+                                                 (3, (64, 64), 4), (5, (48, 16), 3), (8, (64, 64), 2),
+                                                 (9, (32, 32), 2)])
 @pytest.mark.parametrize("standardize", [False, True])
-def test_rqspline_predict(ndim, hidden, layers, standardize):
+@pytest.mark.parametrize("path", [_lib.HB_PATH_AUTO, _lib.HB_PATH_SIMT_GENERIC])
+def test_rqspline_predict(ndim, hidden, layers, standardize, path):
+    """AUTO uses the register fast path for two hidden layers / ndim <= 8 / 8 bins and the generic
+    kernel otherwise; HB_PATH_SIMT_GENERIC forces the generic kernel."""
+    if path == _lib.HB_PATH_SIMT_GENERIC and len(hidden) != 2:
+        pytest.skip("generic kernel is already the AUTO choice")
     m = util.make_rqspline(ndim, layers, 8, hidden, seed=ndim + layers, standardize=standardize)
+    m.kernel_path = path
     x = samples(1500, ndim, seed=3, scale=2.0)
     x[:20] *= 8.0  # some features outside the spline range -> linear tails
     x[5, 0] = 10.0
