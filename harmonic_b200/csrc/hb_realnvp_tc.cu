@@ -1,26 +1,39 @@
 // tcgen05 RealNVP kernel (sm_100a): fused flow evaluation + per-chain fold.
 //
 // Replaces harmonic/flows.py:41-116,159-180 (tfp-jax RealNVP log_prob) + harmonic/model.py:222-235
-// + harmonic/evidence.py:278-352 for the shapes the tensor path supports (ndim = 64 today).
+// + harmonic/evidence.py:278-352 for the shapes the tensor path supports (ndim = 64, <= 8 coupling
+// layers; everything else runs on the CUDA-core kernels).
 //
 // Mapping.  One persistent CTA per SM, 320 threads:
-//   warps 0-3 / 4-7 : two "epilogue" warpgroups; each owns one 128-sample tile at a time, one sample
-//                     per thread (TMEM lane = sample), y[ndim] in registers through all layers
-//   warp 8          : weight producer: streams each layer's pre-split weight image (hi/lo TF32,
-//                     UMMA canonical no-swizzle K-major layout, built once on the host) from L2 into
-//                     a 4-slot shared-memory ring with cp.async.bulk + mbarrier
-//   warp 9          : TMEM allocator + single-thread tcgen05.mma issuer
-// Per coupling layer and tile:   GEMM1  H[128x128]  = y0[128xd]  . W0[dx128]      (A, B from smem)
-//                                E1     h = leaky_relu(H + b0), split hi/lo, back to TMEM
-//                                GEMM2  O[128xN2]   = h[128x128] . [Wt|Ws]        (A from TMEM)
-//                                E2     shift/scale epilogue on y1, log-det
+//   warps 0-3 / 4-7 : two epilogue warpgroups; each owns one 128-sample tile at a time, one sample
+//                     per thread (TMEM lane = sample), y[64] in registers through all layers
+//   warp 8          : weight producer: streams the pre-split weight image (hi/lo TF32, UMMA canonical
+//                     no-swizzle K-major layout, built once on the host) from L2 into an 8-slot ring
+//                     of 16 KiB chunks with cp.async.bulk + mbarrier
+//   warps 9, 10     : tcgen05.mma issuers, one per tile (warp 9 also allocates TMEM); warp-uniform
+//                     straight-line program with blocking mbarrier waits, one elected lane issues
+//
+// Per coupling layer and tile
+//   GEMM1  H[128x128] = [x(0..31) | new(0..6) | 1] . W0'        A, B from shared memory, K = 40
+//   E1     h = leaky_relu(H), split hi/lo, back to TMEM          four 32-column quarters
+//   GEMM2  O[128xN2] += h[:, quarter] . [Wt|Ws][quarter, :]      A from TMEM, one K = 32 step per quarter
+//   E2     shift / softplus-clip scale epilogue on y1, log-det
 // Each GEMM is 3xTF32: a.w ~= a_lo.w_hi + a_hi.w_lo + a_hi.w_hi with FP32 accumulation in TMEM
 // (hi = top 19 bits, lo = exact remainder), so per-sample ln phi keeps ~FP32 accuracy.
-// TMEM (512 columns), per tile t at column 256 t:  P (128: H, then h_hi in place) | Q (64: h_lo of
-// the hidden half in flight) | O (64: GEMM2 accumulators).  GEMM2 runs as two K-halves so that only
-// half of h_lo has to live in TMEM; the epilogue of the second half overlaps the first half's MMAs.
-// The MMA thread issues whichever tile's next GEMM is ready (layers stay in lock-step so that the
-// weight ring is consumed in order), so one tile's epilogue overlaps the other tile's tensor work.
+//
+// GEMM1 without re-staging activations.  The flow permutes by one position per layer
+// (harmonic/flows.py:65-66), so layer l conditions on ORIGINAL features l .. l+31: the features below
+// 32 are still the raw (standardised) inputs, and the j < l features 32+j were frozen by layer j's
+// epilogue.  The A operand is therefore written ONCE per tile -- the raw x(0..31) -- plus one new
+// column per layer; each layer's W0 is stored shifted by l rows ("main", K = 32) next to a K = 8
+// "correction" block whose rows multiply the new columns and a constant-one column that carries the
+// bias b0.  The main part of layer l+1 is issued as soon as layer l's last GEMM2 quarter has drained,
+// i.e. it runs under layer l's epilogue; only the 3-MMA correction waits for the new column.
+//
+// GEMM2 is pipelined with E1 at quarter granularity: quarter q of h_lo goes to Q buffer q & 1, its
+// GEMM2 step runs while the epilogue computes quarter q + 1.
+// TMEM (512 columns), per tile t at column 256 t:  P (128: H, then h_hi in place) | Q (2 x 32: h_lo
+// quarters) | O (64: GEMM2 accumulators).
 #include <math.h>
 #include <string.h>
 
@@ -35,27 +48,29 @@ namespace tc {
 constexpr int D = 64;
 constexpr int DH = 32;        // d = conditioning width (round(D/2))
 constexpr int U = 32;         // transformed width
-constexpr int HID = 128;
 constexpr int TILE = 128;
 constexpr int NWG = 2;        // epilogue warpgroups = tiles in flight
-constexpr int THREADS = NWG * 128 + 64;
-constexpr int SLOT_BYTES = 32768;
-constexpr int NSLOTS = 4;
-constexpr int MAX_TC_LAYERS = 16;
+constexpr int THREADS = NWG * 128 + 96;  // + producer warp + one MMA warp per tile
+constexpr int SLOT_BYTES = 16384;
+constexpr int NSLOTS = 8;
+constexpr int MAX_TC_LAYERS = 8;  // one K = 8 correction step holds 7 new columns + the bias column
+constexpr int KA = 40;            // A operand columns: 32 raw + 7 new + 1 constant
+constexpr int A_HALF = KA / 4 * 2048;  // bytes of the hi (or lo) half of a tile's A operand
+constexpr int A_TILE = 2 * A_HALF;
 
 // shared memory carve-up (bytes)
 constexpr int SM_RING = 0;
-constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;            // per WG: hi 16 KB | lo 16 KB
-constexpr int SM_BIAS = SM_A1 + NWG * 32768;                    // MAX_TC_LAYERS * 192 floats
-constexpr int SM_PRE = SM_BIAS + MAX_TC_LAYERS * 192 * 4;       // standardisation: inv_amp[D], -offset*inv_amp[D]
-constexpr int SM_BAR = SM_PRE + 2 * D * 4;                      // mbarriers
-constexpr int SM_MISC = SM_BAR + 256;                           // tmem ptr, fold scratch
+constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;       // per tile: hi | lo
+constexpr int SM_BIAS = SM_A1 + NWG * A_TILE;              // b2: MAX_TC_LAYERS * 64 floats
+constexpr int SM_PRE = SM_BIAS + MAX_TC_LAYERS * 64 * 4;   // standardisation: inv_amp[D], -offset*inv_amp[D]
+constexpr int SM_BAR = SM_PRE + 2 * D * 4;                 // mbarriers
+constexpr int SM_MISC = SM_BAR + 512;                      // tmem ptr, fold scratch
 constexpr int SM_TOTAL = SM_MISC + 256;
 
-// barrier indices (8 bytes each)
+// barrier indices (8 bytes each); per-tile barriers are indexed + tile
 enum {
-  B_WFULL = 0, B_WEMPTY = 4, B_A1FULL = 8, B_HFULL = 10, B_A2A = 12, B_QFREE = 14, B_A2B = 16, B_OFULL = 18,
-  B_COUNT = 20
+  B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = 18, B_A2 = 20 /* [buf][tile] */, B_QFREE = 24 /* [buf][tile] */,
+  B_OFULL = 28, B_COUNT = 30
 };
 
 // TMEM columns (per tile: + 256 * tile)
@@ -63,10 +78,11 @@ constexpr uint32_t TM_P = 0, TM_Q = 128, TM_O = 192, TM_TILE = 256;
 
 struct Params {
   const uint8_t* image;   // weight image: chunks of SLOT_BYTES in consumption order
-  const float* bias;      // per layer 192 floats: b0[128], b2[64]
+  const float* bias;      // per layer 64 floats: bt[32], bs[32]
   const float* pre;       // pre_offset[D], pre_amp[D] or nullptr
   int nlayers;
   int nscaled;
+  int chunks_per_batch;
   float T, sum_log_amp;
   long long nrows;
   long long rows_per_wg;  // contiguous rows per epilogue warpgroup (multiple of TILE)
@@ -186,45 +202,6 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__device__ __forceinline__ float softplus_clip(float a) {
-  float sp = fmaxf(a, 0.f) + log1pf(expf(-fabsf(a)));
-  return fminf(fmaxf(sp, 1e-3f), 1e3f);
-}
-
-template <typename XT>
-__device__ __forceinline__ void load_row(const XT* __restrict__ x, long long ld, long long r, float (&y)[D]);
-
-template <>
-__device__ __forceinline__ void load_row<float>(const float* __restrict__ x, long long ld, long long r,
-                                                float (&y)[D]) {
-  const float* p = x + r * ld;
-  if ((((uintptr_t)p) & 15) == 0) {
-#pragma unroll
-    for (int i = 0; i < D / 4; ++i) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
-      y[4 * i] = v.x; y[4 * i + 1] = v.y; y[4 * i + 2] = v.z; y[4 * i + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < D; ++i) y[i] = __ldg(p + i);
-  }
-}
-template <>
-__device__ __forceinline__ void load_row<double>(const double* __restrict__ x, long long ld, long long r,
-                                                 float (&y)[D]) {
-  const double* p = x + r * ld;
-  if ((((uintptr_t)p) & 15) == 0) {
-#pragma unroll
-    for (int i = 0; i < D / 2; ++i) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(p) + i);
-      y[2 * i] = (float)v.x; y[2 * i + 1] = (float)v.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < D; ++i) y[i] = (float)__ldg(p + i);
-  }
-}
-
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -277,17 +254,54 @@ __device__ __forceinline__ float softplus_clip_fast(float a) {
   return fminf(fmaxf(sp, 1e-3f), 1e3f);  // NaN in -> NaN out is handled by the caller's y1 path
 }
 
-// E1 for one 32-column chunk: h = leaky_relu(H + b0) -> hi (top 19 bits) / lo (exact remainder)
-__device__ __forceinline__ void e1_chunk(uint32_t (&v)[32], uint32_t (&w)[32], const float* b0c) {
+template <typename XT>
+__device__ __forceinline__ void load_row(const XT* __restrict__ x, long long ld, long long r, float (&y)[D]);
+
+template <>
+__device__ __forceinline__ void load_row<float>(const float* __restrict__ x, long long ld, long long r,
+                                                float (&y)[D]) {
+  const float* p = x + r * ld;
+  if ((((uintptr_t)p) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+      y[4 * i] = v.x; y[4 * i + 1] = v.y; y[4 * i + 2] = v.z; y[4 * i + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) y[i] = __ldg(p + i);
+  }
+}
+template <>
+__device__ __forceinline__ void load_row<double>(const double* __restrict__ x, long long ld, long long r,
+                                                 float (&y)[D]) {
+  const double* p = x + r * ld;
+  if ((((uintptr_t)p) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < D / 2; ++i) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(p) + i);
+      y[2 * i] = (float)v.x; y[2 * i + 1] = (float)v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) y[i] = (float)__ldg(p + i);
+  }
+}
+
+// E1 for one 32-column quarter: h = leaky_relu(H) -> hi (top 19 bits) / lo (exact remainder).
+// The bias b0 is already inside H (constant-one column of the A operand).
+__device__ __forceinline__ void e1_quarter(uint32_t (&v)[32], uint32_t (&w)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    float h = __uint_as_float(v[j]) + b0c[j];
+    float h = __uint_as_float(v[j]);
     h = fmaxf(h, 0.01f * h);
     const uint32_t hb = __float_as_uint(h) & 0xffffe000u;
     v[j] = hb;
     w[j] = __float_as_uint(h - __uint_as_float(hb));
   }
 }
+
+__device__ __forceinline__ int layer_chunks(bool scaled) { return scaled ? 7 : 5; }
 
 template <typename XT, typename LT, bool FOLD>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -308,19 +322,20 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOTS; ++i) {
       mbar_init(BAR(B_WFULL + i), 1);
-      mbar_init(BAR(B_WEMPTY + i), 1);
+      mbar_init(BAR(B_WEMPTY + i), NWG);  // both MMA warps release a slot
     }
     for (int t = 0; t < NWG; ++t) {
       mbar_init(BAR(B_A1FULL + t), 128);
       mbar_init(BAR(B_HFULL + t), 1);
-      mbar_init(BAR(B_A2A + t), 128);
+      mbar_init(BAR(B_A2 + t), 128);
+      mbar_init(BAR(B_A2 + 2 + t), 128);
       mbar_init(BAR(B_QFREE + t), 1);
-      mbar_init(BAR(B_A2B + t), 128);
+      mbar_init(BAR(B_QFREE + 2 + t), 1);
       mbar_init(BAR(B_OFULL + t), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < nl * 192; i += THREADS) bias_s[i] = P.bias[i];
+  for (int i = threadIdx.x; i < nl * 64; i += THREADS) bias_s[i] = P.bias[i];
   for (int i = threadIdx.x; i < D; i += THREADS) {
     const float inv = P.pre ? 1.f / P.pre[D + i] : 1.f;
     pre_s[i] = inv;
@@ -339,115 +354,125 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 8) {
-    // ===== weight producer =====
+    // ===== weight producer: the image is one batch worth of chunks, replayed every batch =====
     if (lane == 0) {
       uint32_t g = 0;
       for (int b = 0; b < P.nbatches; ++b) {
         const uint8_t* src = P.image;
-        for (int l = 0; l < nl; ++l) {
-          const int nch = (l < P.nscaled) ? 3 : 2;
-          for (int c = 0; c < nch; ++c, ++g) {
-            const uint32_t slot = g & (NSLOTS - 1), use = g / NSLOTS;
-            mbar_wait(BAR(B_WEMPTY + slot), (use & 1) ^ 1);
-            mbar_expect_tx(BAR(B_WFULL + slot), SLOT_BYTES);
-            bulk_g2s(sbase + SM_RING + slot * SLOT_BYTES, src, SLOT_BYTES, BAR(B_WFULL + slot));
-            src += SLOT_BYTES;
-          }
+        for (int c = 0; c < P.chunks_per_batch; ++c, ++g) {
+          const uint32_t slot = g & (NSLOTS - 1), use = g / NSLOTS;
+          mbar_wait(BAR(B_WEMPTY + slot), (use & 1) ^ 1);
+          mbar_expect_tx(BAR(B_WFULL + slot), SLOT_BYTES);
+          bulk_g2s(sbase + SM_RING + slot * SLOT_BYTES, src, SLOT_BYTES, BAR(B_WFULL + slot));
+          src += SLOT_BYTES;
         }
       }
     }
-  } else if (warp == 9) {
-    // ===== MMA issuer: the whole warp runs the (warp-uniform) scheduling loop so that descriptors
-    // stay in uniform registers; one elected lane issues.  Within a layer it serves whichever
-    // tile is ready.
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+  } else if (warp >= 9) {
+    // ===== MMA issuers: warp 9 serves tile 0, warp 10 tile 1.  Each runs a straight-line program
+    // per layer with blocking mbarrier waits; the whole warp executes it (warp-uniform, so the
+    // descriptors stay in uniform registers) and one elected lane issues.  A weight slot is
+    // released when both warps have committed on it (WEMPTY expects two arrivals).
+    const int t = warp - 9;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
     const uint32_t id128 = make_idesc(128), id64 = make_idesc(64), id32 = make_idesc(32);
+    const uint32_t a_x = sbase + SM_A1 + t * A_TILE;           // raw features, K-chunks 0..7
+    const uint32_t a_new = a_x + 8 * 2048;                      // new columns + constant one
+    const uint64_t adx_hi = make_desc(a_x, 2048, 128), adx_lo = make_desc(a_x + A_HALF, 2048, 128);
+    const uint64_t adn_hi = make_desc(a_new, 2048, 128), adn_lo = make_desc(a_new + A_HALF, 2048, 128);
+    auto wwait = [&](uint32_t gidx) {
+      mbar_wait(BAR(B_WFULL + (gidx & (NSLOTS - 1))), (gidx / NSLOTS) & 1);
+    };
+    auto chunk_addr = [&](uint32_t gidx) { return sbase + SM_RING + (gidx & (NSLOTS - 1)) * SLOT_BYTES; };
+    auto release = [&](uint32_t gidx) {
+      if (elect_one()) tc_commit(BAR(B_WEMPTY + (gidx & (NSLOTS - 1))));
+      __syncwarp();
+    };
+    // main part of GEMM1 (layer chunks g, g+1): H = x(0..31) . W0main, K = 32
+    auto issue_main = [&](uint32_t g) {
+      wwait(g);
+      wwait(g + 1);
+      tc_fence_after();
+      const uint64_t w01 = make_desc(chunk_addr(g), 2048, 128), w23 = make_desc(chunk_addr(g + 1), 2048, 128);
+      if (elect_one()) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint64_t aa = (pass == 0) ? adx_lo : adx_hi;
+          const uint64_t boff = (pass == 1) ? (uint64_t)(8192 >> 4) : 0;  // lo block of the chunk
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bb = ((k < 2) ? w01 : w23) + boff + (uint64_t)((k & 1) * 256);
+            mma_ss(tb + TM_P, aa + (uint64_t)(k * 256), bb, id128, acc);
+            acc = 1;
+          }
+        }
+      }
+      __syncwarp();
+    };
     uint32_t g = 0, it = 0;
     for (int b = 0; b < P.nbatches; ++b) {
       for (int l = 0; l < nl; ++l, ++it) {
         const bool scaled = l < P.nscaled;
         const uint32_t par = it & 1;
-        const uint32_t s0 = g & (NSLOTS - 1);
-        const uint32_t s1 = (g + 1) & (NSLOTS - 1), s2 = (g + 2) & (NSLOTS - 1);
-        const uint32_t w0 = sbase + SM_RING + s0 * SLOT_BYTES;  // hi [128x32] 16 KB | lo 16 KB
-        const uint32_t lbo2 = (scaled ? 64u : 32u) * 16u;
-        const uint32_t w_hi = sbase + SM_RING + s1 * SLOT_BYTES;
-        const uint32_t w_lo = scaled ? sbase + SM_RING + s2 * SLOT_BYTES : w_hi + 16384;
-        const uint32_t id2 = scaled ? id64 : id32;
-        const uint64_t wd_hi = make_desc(w0, 2048, 128), wd_lo = make_desc(w0 + 16384, 2048, 128);
-        const uint64_t bd_hi = make_desc(w_hi, lbo2, 128), bd_lo = make_desc(w_lo, lbo2, 128);
+        // ---- GEMM1: (main, unless issued early) + correction
+        mbar_wait(BAR(B_A1FULL + t), par);
+        if (l == 0) issue_main(g);
+        wwait(g + 2);
+        tc_fence_after();
+        {
+          const uint64_t wc = make_desc(chunk_addr(g + 2), 2048, 128);
+          if (elect_one()) {
+            mma_ss(tb + TM_P, adn_lo, wc, id128, 1);
+            mma_ss(tb + TM_P, adn_hi, wc + (uint64_t)(4096 >> 4), id128, 1);
+            mma_ss(tb + TM_P, adn_hi, wc, id128, 1);
+            tc_commit(BAR(B_HFULL + t));
+            tc_commit(BAR(B_WEMPTY + (g & (NSLOTS - 1))));
+            tc_commit(BAR(B_WEMPTY + ((g + 1) & (NSLOTS - 1))));
+            tc_commit(BAR(B_WEMPTY + ((g + 2) & (NSLOTS - 1))));
+          }
+          __syncwarp();
+        }
+        // ---- GEMM2: four K = 32 quarters, each as soon as its half of E1 has landed
+        const uint32_t n2 = scaled ? 64u : 32u;
+        const uint32_t lbo2 = n2 * 16u;
+        const uint32_t qbytes = 8 * lbo2;  // one quarter of hi (or lo): 8 K-chunks
         const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
-        mbar_wait(BAR(B_WFULL + s0), (g / NSLOTS) & 1);
-        bool w2_ready = false, w0_released = false;
-        int stage0 = 0, stage1 = 0;  // 0: GEMM1, 1: GEMM2 first half, 2: GEMM2 second half, 3: done
-        while (stage0 < 3 || stage1 < 3) {
+        const uint32_t id2 = scaled ? id64 : id32;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t gw = g + 3 + (scaled ? q : (q >> 1));
+          mbar_wait(BAR(B_A2 + 2 * (q & 1) + t), (uint32_t)(q >> 1));
+          wwait(gw);
+          tc_fence_after();
+          const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? 2 * qbytes : 0);
+          const uint64_t bd_hi = make_desc(wbase, lbo2, 128), bd_lo = make_desc(wbase + qbytes, lbo2, 128);
+          const uint32_t a_lo = tb + TM_Q + 32 * (q & 1), a_hi = tb + TM_P + 32 * q;
+          if (elect_one()) {
+            uint32_t acc = q ? 1u : 0u;
 #pragma unroll
-          for (int t = 0; t < NWG; ++t) {
-            const int stage = t ? stage1 : stage0;
-            const uint32_t tb = tmem_u + t * TM_TILE;
-            if (stage == 0) {
-              if (!__all_sync(0xffffffffu, mbar_test(BAR(B_A1FULL + t), par))) continue;
-              tc_fence_after();
-              // GEMM1: H = y0 . W0 (K = 32 -> 4 k-steps, three split passes, small terms first)
-              const uint32_t a_hi = sbase + SM_A1 + t * 32768;
-              const uint64_t ad_hi = make_desc(a_hi, 2048, 128), ad_lo = make_desc(a_hi + 16384, 2048, 128);
-              if (elect_one()) {
-                uint32_t acc = 0;
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t aa = (pass == 0) ? a_lo : a_hi;
+              const uint64_t bb = (pass == 1) ? bd_lo : bd_hi;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                  const uint64_t aa = (pass == 0) ? ad_lo : ad_hi;
-                  const uint64_t bb = (pass == 1) ? wd_lo : wd_hi;
-#pragma unroll
-                  for (int k = 0; k < DH / 8; ++k) {
-                    mma_ss(tb + TM_P, aa + (uint64_t)(k * 256), bb + (uint64_t)(k * 256), id128, acc);
-                    acc = 1;
-                  }
-                }
-                tc_commit(BAR(B_HFULL + t));
+              for (int k = 0; k < 4; ++k) {
+                mma_ts(tb + TM_O, aa + k * 8, bb + (uint64_t)k * kstep2, id2, acc);
+                acc = 1;
               }
-              __syncwarp();
-            } else if (stage <= 2) {
-              const int half = stage - 1;
-              if (!__all_sync(0xffffffffu, mbar_test(BAR((half ? B_A2B : B_A2A) + t), par))) continue;
-              if (!w2_ready) {
-                mbar_wait(BAR(B_WFULL + s1), ((g + 1) / NSLOTS) & 1);
-                if (scaled) mbar_wait(BAR(B_WFULL + s2), ((g + 2) / NSLOTS) & 1);
-                w2_ready = true;
-              }
-              tc_fence_after();
-              // GEMM2 half: O (+)= h[:, 64 half ..] . W2[64 half .., :]  (A from TMEM, K = 64)
-              if (elect_one()) {
-                uint32_t acc = half ? 1u : 0u;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                  const uint32_t aa = (pass == 0) ? tb + TM_Q : tb + TM_P + half * 64;
-                  const uint64_t bb = ((pass == 1) ? bd_lo : bd_hi) + (uint64_t)(half * 8) * kstep2;
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    mma_ts(tb + TM_O, aa + k * 8, bb + (uint64_t)k * kstep2, id2, acc);
-                    acc = 1;
-                  }
-                }
-                tc_commit(BAR((half ? B_OFULL : B_QFREE) + t));
-              }
-              __syncwarp();
-            } else {
-              continue;
             }
-            if (t) ++stage1; else ++stage0;
+            tc_commit(BAR(B_QFREE + 2 * (q & 1) + t));
+            if (q == 3) tc_commit(BAR(B_OFULL + t));
+            if (scaled || (q & 1)) tc_commit(BAR(B_WEMPTY + (gw & (NSLOTS - 1))));
           }
-          if (!w0_released && stage0 >= 1 && stage1 >= 1) {  // both GEMM1s issued: free W0's slot
-            if (elect_one()) tc_commit(BAR(B_WEMPTY + s0));
-            __syncwarp();
-            w0_released = true;
-          }
+          __syncwarp();
         }
-        if (elect_one()) {
-          tc_commit(BAR(B_WEMPTY + s1));
-          if (scaled) tc_commit(BAR(B_WEMPTY + s2));
+        g += layer_chunks(scaled);
+        // ---- early main part of the next layer: runs under this layer's E2.  P is GEMM2's A operand
+        // until the last quarter has drained.
+        if (l + 1 < nl) {
+          mbar_wait(BAR(B_OFULL + t), par);
+          issue_main(g);
         }
-        __syncwarp();
-        g += scaled ? 3 : 2;
       }
     }
   } else {
@@ -458,7 +483,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     const uint32_t tm_p = tmem_base + lane_base + wg * TM_TILE + TM_P;
     const uint32_t tm_q = tmem_base + lane_base + wg * TM_TILE + TM_Q;
     const uint32_t tm_o = tmem_base + lane_base + wg * TM_TILE + TM_O;
-    uint8_t* a1 = smem + SM_A1 + wg * 32768;
+    uint8_t* a1 = smem + SM_A1 + wg * A_TILE;
     double* scratch = reinterpret_cast<double*>(smem + SM_MISC + 16) + wg * 12;
     const int flusher = blockIdx.x * NWG + wg;
     const long long row_lo = (long long)flusher * P.rows_per_wg;
@@ -485,63 +510,57 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       }
 #pragma unroll
       for (int i = 0; i < D; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
+      // ---- A operand, written once per tile: raw features 0..31 (hi | lo), zeroed new columns,
+      // constant one in column 39.  (GEMM1 of the previous tile has completed: its HFULL was waited.)
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) {
+        uint4 hi, lo;
+        uint32_t* ph = &hi.x;
+        uint32_t* pl = &lo.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float v = y[4 * c + q];
+          const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
+          ph[q] = hb;
+          pl[q] = __float_as_uint(v - __uint_as_float(hb));
+        }
+        *reinterpret_cast<uint4*>(a1 + c * 2048 + tid * 16) = hi;
+        *reinterpret_cast<uint4*>(a1 + A_HALF + c * 2048 + tid * 16) = lo;
+      }
+      {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = z;
+        *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x3f800000u);
+        *reinterpret_cast<uint4*>(a1 + A_HALF + 8 * 2048 + tid * 16) = z;
+        *reinterpret_cast<uint4*>(a1 + A_HALF + 9 * 2048 + tid * 16) = z;
+      }
       float ldj = 0.f;
       for (int l = 0; l < nl; ++l, ++it) {
         const uint32_t par = it & 1;
         const bool scaled = l < P.nscaled;
-        const float* b0 = bias_s + l * 192;
-        const float* b2 = b0 + 128;
-        // ---- A1: y0 split hi/lo into the canonical smem layout (row tid, 4 k per 16-byte chunk)
-#pragma unroll
-        for (int c = 0; c < DH / 4; ++c) {
-          uint4 hi, lo;
-          uint32_t* ph = &hi.x;
-          uint32_t* pl = &lo.x;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float v = y[4 * c + q];
-            const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
-            ph[q] = hb;
-            pl[q] = __float_as_uint(v - __uint_as_float(hb));
-          }
-          *reinterpret_cast<uint4*>(a1 + c * 2048 + tid * 16) = hi;
-          *reinterpret_cast<uint4*>(a1 + 16384 + c * 2048 + tid * 16) = lo;
-        }
+        const float* b2 = bias_s + l * 64;
         fence_proxy_async();
         tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
         mbar_arrive(BAR(B_A1FULL + wg));
-        // ---- E1: h = leaky_relu(H + b0) -> hi in place, lo into Q; two 64-column halves
+        // ---- E1: four quarters; quarter q's h_lo goes to Q buffer q & 1 and its GEMM2 step runs
+        // while quarter q + 1 is computed
         mbar_wait(BAR(B_HFULL + wg), par);
         tc_fence_after();
-        {
-          uint32_t v[32], w[32];
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {  // first hidden half
-            tmem_ld32(tm_p + c * 32, v);
-            tmem_ld_wait();
-            e1_chunk(v, w, b0 + c * 32);
-            tmem_st32(tm_p + c * 32, v);
-            tmem_st32(tm_q + c * 32, w);
+        for (int q = 0; q < 4; ++q) {
+          uint32_t v[32], w[32];
+          tmem_ld32(tm_p + q * 32, v);
+          tmem_ld_wait();
+          e1_quarter(v, w);
+          tmem_st32(tm_p + q * 32, v);
+          if (q >= 2) {  // Q buffer q & 1 is still GEMM2 quarter q - 2's operand until then
+            mbar_wait(BAR(B_QFREE + 2 * (q & 1) + wg), 0);
+            tc_fence_after();
           }
+          tmem_st32(tm_q + (q & 1) * 32, w);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(BAR(B_A2A + wg));
-          // second half: compute chunk 2 while GEMM2's first half still reads Q
-          tmem_ld32(tm_p + 64, v);
-          tmem_ld_wait();
-          e1_chunk(v, w, b0 + 64);
-          tmem_st32(tm_p + 64, v);
-          mbar_wait(BAR(B_QFREE + wg), par);
-          tc_fence_after();
-          tmem_st32(tm_q, w);
-          tmem_ld32(tm_p + 96, v);
-          tmem_ld_wait();
-          e1_chunk(v, w, b0 + 96);
-          tmem_st32(tm_p + 96, v);
-          tmem_st32(tm_q + 32, w);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(BAR(B_A2B + wg));
+          mbar_arrive(BAR(B_A2 + 2 * (q & 1) + wg));
         }
         // ---- E2: y1 = (y1 - shift) / scale, ldj -= sum log scale
         mbar_wait(BAR(B_OFULL + wg), par);
@@ -573,8 +592,16 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             for (int k = 0; k < U; ++k) y[DH + k] -= __uint_as_float(sh[k]) + b2[k];
           }
         }
-        // ---- inverse of tfb.Permute([D-1, 0, .., D-2]): rotate left by one (flows.py:65-66)
         if (l + 1 < nl) {
+          // feature (logical 32) is frozen from here on: it is the new conditioning column l of the
+          // following layers
+          const float v = y[DH];
+          const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
+          const int col = DH + l;
+          uint8_t* dst = a1 + (col >> 2) * 2048 + tid * 16 + (col & 3) * 4;
+          *reinterpret_cast<uint32_t*>(dst) = hb;
+          *reinterpret_cast<uint32_t*>(dst + A_HALF) = __float_as_uint(v - __uint_as_float(hb));
+          // inverse of tfb.Permute([D-1, 0, .., D-2]): rotate left by one (flows.py:65-66)
           const float y0 = y[0];
 #pragma unroll
           for (int i = 0; i < D - 1; ++i) y[i] = y[i + 1];
@@ -612,7 +639,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
-// host side: weight image (hi/lo split, canonical K-major no-swizzle layout)
+// host side: weight image (hi/lo split, canonical K-major no-swizzle layout, 16 KiB chunks)
 // ---------------------------------------------------------------------------------------------
 static inline void split_tf32(float v, float* hi, float* lo) {
   uint32_t b;
@@ -622,13 +649,9 @@ static inline void split_tf32(float v, float* hi, float* lo) {
   *lo = v - *hi;
 }
 
-// writes B[n][k] = W[k*ldw + n] (flax kernel is (in, out)) for n < N, k < K into hi/lo blocks
-static void pack_b(float* hi, float* lo, int N, int K, const float* W, int ldw, int n0, int nvalid) {
-  for (int n = 0; n < nvalid; ++n)
-    for (int k = 0; k < K; ++k) {
-      const size_t off = (size_t)((n0 + n) / 8) * 32 + (size_t)((n0 + n) % 8) * 4 + (size_t)(k / 4) * (N * 4) + (k % 4);
-      split_tf32(W[(size_t)k * ldw + n], &hi[off], &lo[off]);
-    }
+// element (n, k) of a K-major [N x K] block in the canonical no-swizzle layout, in floats
+static inline size_t kmajor_off(int N, int n, int k) {
+  return (size_t)(n / 8) * 32 + (size_t)(n % 8) * 4 + (size_t)(k / 4) * (N * 4) + (k % 4);
 }
 
 int realnvp_tc_prepare(Flow* f) {
@@ -638,38 +661,61 @@ int realnvp_tc_prepare(Flow* f) {
   const int nl = f->nlayers;
   if (nl > tc::MAX_TC_LAYERS) return HB_OK;
   const int d = f->d, u = f->u;
+  const size_t CF = tc::SLOT_BYTES / 4;  // floats per chunk
   size_t nchunks = 0;
-  for (int l = 0; l < nl; ++l) nchunks += (l < ds.n_scaled) ? 3 : 2;
-  std::vector<float> img(nchunks * (tc::SLOT_BYTES / 4), 0.f);
-  std::vector<float> bias((size_t)nl * 192, 0.f);
+  for (int l = 0; l < nl; ++l) nchunks += (l < ds.n_scaled) ? 7 : 5;
+  std::vector<float> img(nchunks * CF, 0.f);
+  std::vector<float> bias((size_t)nl * 64, 0.f);
   const float* w = f->host_weights.data();
   size_t ch = 0;
   for (int l = 0; l < nl; ++l) {
     const bool scaled = l < ds.n_scaled;
-    const float* W0 = w + f->layer_off[l];
+    const float* W0 = w + f->layer_off[l];       // [d][128]
     const float* b0 = W0 + (size_t)d * 128;
-    const float* Wt = b0 + 128;
+    const float* Wt = b0 + 128;                  // [128][u]
     const float* bt = Wt + (size_t)128 * u;
     const float* Ws = bt + u;
     const float* bs = Ws + (size_t)128 * u;
-    float* c0 = img.data() + ch * (tc::SLOT_BYTES / 4);
-    pack_b(c0, c0 + 4096, 128, d, W0, 128, 0, 128);  // hi 16 KB | lo 16 KB
-    ++ch;
-    if (scaled) {
-      float* ca = img.data() + ch * (tc::SLOT_BYTES / 4);
-      float* cb = ca + tc::SLOT_BYTES / 4;
-      pack_b(ca, cb, 64, 128, Wt, u, 0, u);
-      pack_b(ca, cb, 64, 128, Ws, u, u, u);
-      ch += 2;
-    } else {
-      float* ca = img.data() + ch * (tc::SLOT_BYTES / 4);
-      pack_b(ca, ca + 4096, 32, 128, Wt, u, 0, u);
-      ++ch;
+    // GEMM1 main: A column i (original feature i < 32) meets W0 row i - l (zero for i < l).
+    // chunk 0: k = 0..15 (hi 8 KB | lo 8 KB), chunk 1: k = 16..31
+    for (int i = 0; i < 32; ++i) {
+      float* c = img.data() + (ch + (i >> 4)) * CF;
+      for (int n = 0; n < 128; ++n) {
+        const float v = (i >= l) ? W0[(size_t)(i - l) * 128 + n] : 0.f;
+        const size_t off = kmajor_off(128, n, i & 15);
+        split_tf32(v, &c[off], &c[2048 + off]);
+      }
     }
-    for (int j = 0; j < 128; ++j) bias[(size_t)l * 192 + j] = b0[j];
-    for (int k = 0; k < u; ++k) bias[(size_t)l * 192 + 128 + k] = bt[k];
+    // GEMM1 correction (chunk 2): k = 0..6 <-> frozen feature 32 + j meets W0 row 32 - l + j (j < l),
+    // k = 7 <-> constant one column carrying the bias b0.  hi 4 KB | lo 4 KB
+    {
+      float* c = img.data() + (ch + 2) * CF;
+      for (int k = 0; k < 8; ++k)
+        for (int n = 0; n < 128; ++n) {
+          float v = 0.f;
+          if (k == 7) v = b0[n];
+          else if (k < l) v = W0[(size_t)(32 - l + k) * 128 + n];
+          const size_t off = kmajor_off(128, n, k);
+          split_tf32(v, &c[off], &c[1024 + off]);
+        }
+    }
+    // GEMM2: B[n][k] = [Wt | Ws][k][n]; one K = 32 quarter = hi block | lo block
+    const int N2 = scaled ? 64 : 32;
+    const size_t qf = (size_t)8 * N2 * 4;  // floats per quarter block (8 K-chunks)
+    for (int q = 0; q < 4; ++q) {
+      float* c = scaled ? img.data() + (ch + 3 + q) * CF : img.data() + (ch + 3 + (q >> 1)) * CF + (q & 1) * 2 * qf;
+      for (int kk = 0; kk < 32; ++kk)
+        for (int n = 0; n < N2; ++n) {
+          const int k = 32 * q + kk;
+          const float v = (n < u) ? Wt[(size_t)k * u + n] : Ws[(size_t)k * u + (n - u)];
+          const size_t off = kmajor_off(N2, n, kk);
+          split_tf32(v, &c[off], &c[qf + off]);
+        }
+    }
+    ch += scaled ? 7 : 5;
+    for (int k = 0; k < u; ++k) bias[(size_t)l * 64 + k] = bt[k];
     if (scaled)
-      for (int k = 0; k < u; ++k) bias[(size_t)l * 192 + 128 + u + k] = bs[k];
+      for (int k = 0; k < u; ++k) bias[(size_t)l * 64 + u + k] = bs[k];
   }
   const size_t img_bytes = img.size() * 4, bias_bytes = bias.size() * 4;
   HB_CUDA(cudaMalloc(&f->tc_image, img_bytes + bias_bytes));
@@ -719,6 +765,7 @@ int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, l
   P.nscaled = f->desc.n_scaled;
   P.T = T;
   P.sum_log_amp = f->sum_log_amp;
+  P.chunks_per_batch = (int)(f->tc_image_bytes / tc::SLOT_BYTES);
   P.nrows = n;
   P.rows_per_wg = rpw;
   P.nbatches = (int)(rpw / tc::TILE);
