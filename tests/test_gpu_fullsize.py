@@ -130,3 +130,28 @@ def test_cfg2_cfg3_full_size_streaming_and_subset_oracle(name):
         got = model.predict(x[c * per:c * per + k]).cpu().numpy()
         util.check_predict(model, xs, got)
     assert part[:, 2].sum() == nch * per
+
+
+def test_host_staging_multi_chunk_matches_device_resident():
+    """Host (float64, pageable) chains larger than one 256 MB staging chunk: the double-buffered
+    H2D pipeline must give the same statistics as the device-resident path, and host predict must
+    chunk correctly above 2^20 rows."""
+    import torch
+    model = wl.make_model("cfg4")
+    nch, per = 60, 20000  # 1.2e6 rows x 64 float64 = 614 MB -> 3 staging chunks
+    x, lnp = wl.device_data("cfg4", nch, per, torch.device("cuda", 0), seed=3)
+    start = [i * per for i in range(nch + 1)]
+    xh = x.double().cpu().numpy()
+    lh = lnp.double().cpu().numpy()
+    ch = hm.Chains.from_arrays(xh, lh, start)
+    ev_h = hm.Evidence(nch, model)
+    ev_h.add_chains(ch)
+    ev_d = hm.Evidence(nch, model)
+    ev_d.add_chains(hm.Chains.from_arrays(x, lnp, start))
+    assert ev_h.ln_evidence_inv == pytest.approx(ev_d.ln_evidence_inv, abs=1e-6)
+    assert ev_h.ln_evidence_inv_var == pytest.approx(ev_d.ln_evidence_inv_var, abs=1e-4)
+    np.testing.assert_array_equal(ev_h.nsamples_per_chain, ev_d.nsamples_per_chain)
+    p_h = model.predict(xh)  # > 2^20 rows -> two predict chunks
+    p_d = model.predict(x).cpu().numpy()
+    assert p_h.shape == (nch * per,)
+    np.testing.assert_allclose(p_h, p_d, rtol=0, atol=0)
