@@ -208,8 +208,10 @@ struct Fold {
     }
   }
 
-  // Feed one tile [t0, t1) of the flusher's rows. Thread owns rows t0 + tid*R + q, q < R.
-  template <int R>
+  // Feed one tile [t0, t1) of the flusher's rows.  Thread owns R rows in groups of V consecutive
+  // rows: row(q) = t0 + (q / V) * NT * V + tid * V + q % V  (V = R: R consecutive rows per thread;
+  // V = 4, R = 8: two fully coalesced float4 loads per thread).
+  template <int R, int V = R>
   __device__ __forceinline__ void tile(long long t0, long long t1, const float (&lnpred)[R],
                                        const float (&lnpost)[R]) {
     if (t1 - t0 == (long long)NT * R && t1 <= cur_end) {
@@ -225,12 +227,12 @@ struct Fold {
       return;
     }
     long long seg_begin = t0;
-    const long long r0 = t0 + (long long)tid * R;
+    const long long r0 = t0 + (long long)tid * V;
     while (true) {
       const long long seg_end = (t1 < cur_end) ? t1 : cur_end;
 #pragma unroll
       for (int q = 0; q < R; ++q) {
-        const long long r = r0 + q;
+        const long long r = r0 + (long long)(q / V) * NT * V + (q % V);
         if (r >= seg_begin && r < seg_end) sample(lnpred[q], lnpost[q]);
       }
       if (cur_chain < p.nch && cur_end <= t1) {
