@@ -32,8 +32,9 @@ def make_model(name):
         return util.make_realnvp(64, 2, 4, seed=4, standardize=True, temperature=0.8, ws=0.3)
     if name == "cfg3":
         return util.make_realnvp(5, 6, 2, seed=3, standardize=True, temperature=0.9, ws=0.3)
-    if name == "cfg1":
-        return util.make_realnvp(5, 2, 4, seed=1, standardize=True, temperature=0.8, ws=0.3)
+    if name == "cfg1":  # the trained fixture (tests/golden/make_cfg1_flow.py)
+        from tests.test_cfg1_e2e import load_cfg1_model
+        return load_cfg1_model(0.8)
     if name == "cfg2":
         return util.make_rqspline(2, 8, 8, (64, 64), seed=2, standardize=False, temperature=0.9, ws=0.15)
     raise ValueError(name)
