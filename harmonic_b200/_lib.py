@@ -58,6 +58,8 @@ SIGNATURES = {
                                             C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "hb_accum_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_accum_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_accum_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hb_accum_merge_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "hb_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(Result), C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p]),
     "hb_finalize_realspace": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,

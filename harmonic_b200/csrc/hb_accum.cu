@@ -139,6 +139,34 @@ __global__ void merge_kernel(ChainState* __restrict__ state, double* __restrict_
   }
 }
 
+// fold nranks packed blocks ([4n partials | 8 globals], block r at packed + r*stride) in rank order
+__global__ void merge_packed_kernel(ChainState* __restrict__ state, double* __restrict__ globals,
+                                    const double* __restrict__ packed, long long stride, int nranks,
+                                    long long n) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) {
+    ChainState st = state[c];
+    for (int r = 0; r < nranks; ++r) {
+      const double* part = packed + (long long)r * stride;
+      merge_pair(st.m, st.s, part[4 * c + 0], part[4 * c + 1]);
+      st.n += part[4 * c + 2];
+      st.nnan += part[4 * c + 3];
+    }
+    state[c] = st;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < G_N) {
+    const int k = threadIdx.x;
+    double acc = globals[k];
+    for (int r = 0; r < nranks; ++r) {
+      const double o = packed[(long long)r * stride + 4 * n + k];
+      if (k < 2) acc += o;
+      else if (k & 1) acc = fmin(acc, o);
+      else acc = fmax(acc, o);
+    }
+    globals[k] = acc;
+  }
+}
+
 __global__ void reset_globals_kernel(double* g) {
   const int k = threadIdx.x;
   if (k < G_N) g[k] = (k < 2) ? 0.0 : ((k & 1) ? CUDART_INF : -CUDART_INF);
@@ -632,6 +660,50 @@ int hb_accum_merge(hb_accum* h, const double* partials, const double* globals) {
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(dpart);
   if (dg) cudaFree(dg);
+  HB_CUDA(e);
+  return HB_OK;
+}
+
+int hb_accum_pack(hb_accum* h, double* dst, int mem, void* stream) {
+  HB_REQUIRE(h != nullptr && dst != nullptr, "hb_accum_pack: NULL argument");
+  Accum* acc = reinterpret_cast<Accum*>(h);
+  HB_CUDA(cudaSetDevice(acc->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const cudaMemcpyKind kind = mem == HB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  HB_CUDA(cudaMemcpyAsync(dst, acc->state, acc->nchains * sizeof(ChainState), kind, st));
+  HB_CUDA(cudaMemcpyAsync(dst + 4 * acc->nchains, acc->globals, G_N * sizeof(double), kind, st));
+  if (mem != HB_MEM_DEVICE) HB_CUDA(cudaStreamSynchronize(st));
+  return HB_OK;
+}
+
+int hb_accum_merge_packed(hb_accum* h, int nranks, const double* packed, int64_t stride, int mem,
+                          void* stream) {
+  HB_REQUIRE(h != nullptr && packed != nullptr && nranks >= 1, "hb_accum_merge_packed: bad argument");
+  Accum* acc = reinterpret_cast<Accum*>(h);
+  HB_REQUIRE(stride >= 4 * acc->nchains + G_N, "hb_accum_merge_packed: stride too small");
+  HB_CUDA(cudaSetDevice(acc->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const double* src = packed;
+  double* tmp = nullptr;
+  if (mem != HB_MEM_DEVICE) {
+    const size_t bytes = (size_t)nranks * stride * sizeof(double);
+    HB_CUDA(cudaMalloc(&tmp, bytes));
+    cudaError_t e = cudaMemcpyAsync(tmp, packed, bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+      cudaFree(tmp);
+      return cuda_fail(e, "H2D", __FILE__, __LINE__);
+    }
+    src = tmp;
+  }
+  const int threads = 256;
+  merge_packed_kernel<<<(int)((acc->nchains + threads - 1) / threads), threads, 0, st>>>(
+      acc->state, acc->globals, src, stride, nranks, acc->nchains);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (tmp) {
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+  }
   HB_CUDA(e);
   return HB_OK;
 }

@@ -236,23 +236,36 @@ class Evidence:
         self.check_basic_diagnostic()
 
     def _finish_call(self, lib, acc, comm):
-        part = np.empty((self.nchains, 4), dtype=np.float64)
-        glob = np.empty(8, dtype=np.float64)
         fin = acc
         if comm is not None:
-            _lib.check(lib.hb_accum_export(acc, part.ctypes.data, glob.ctypes.data))
-            self._partials = part
-            gathered = _allgather(np.concatenate([part.reshape(-1), glob]), comm)
+            # the one collective of the path: all-gather of [4*nchains partials | 8 scalars] per rank,
+            # device to device over NCCL (host staging only for CPU backends), then one merge kernel
             if self._acc_global is None:
                 h = _lib.C.c_void_p()
                 _lib.check(lib.hb_accum_create(self.nchains, self.device, _lib.C.byref(h)))
                 self._acc_global = h
             fin = self._acc_global
             _lib.check(lib.hb_accum_reset(fin))
-            for row in gathered:  # fixed rank order -> identical results on every rank
-                p = np.ascontiguousarray(row[:-8])
-                g = np.ascontiguousarray(row[-8:])
-                _lib.check(lib.hb_accum_merge(fin, p.ctypes.data, g.ctypes.data))
+            n = 4 * self.nchains + 8
+            import torch
+            import torch.distributed as dist
+            group = None if comm is True else comm
+            world = dist.get_world_size(group)
+            if dist.get_backend(group) == "nccl":
+                dev = torch.device("cuda", self.device)
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                send = torch.empty(n, dtype=torch.float64, device=dev)
+                _lib.check(lib.hb_stream_sync(None))  # accumulate launches ran on the legacy stream
+                _lib.check(lib.hb_accum_pack(acc, send.data_ptr(), _lib.HB_MEM_DEVICE, stream))
+                recv = torch.empty(world * n, dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(recv, send, group=group)
+                _lib.check(lib.hb_accum_merge_packed(fin, world, recv.data_ptr(), n, _lib.HB_MEM_DEVICE, stream))
+                torch.cuda.current_stream(dev).synchronize()
+            else:
+                send = np.empty(n, dtype=np.float64)
+                _lib.check(lib.hb_accum_pack(acc, send.ctypes.data, _lib.HB_MEM_HOST, None))
+                recv = np.ascontiguousarray(_allgather(send, comm))
+                _lib.check(lib.hb_accum_merge_packed(fin, world, recv.ctypes.data, n, _lib.HB_MEM_HOST, None))
         res = _lib.Result()
         per = np.empty(self.nchains, dtype=np.float64)
         rsum = np.empty(self.nchains, dtype=np.float64)

@@ -153,6 +153,15 @@ int hb_accumulate_precomputed(hb_accum* acc, const void* lnpred, int lnpred_dtyp
 int hb_accum_export(hb_accum* acc, double* partials, double* globals);
 int hb_accum_merge(hb_accum* acc, const double* partials, const double* globals);
 
+/* Packed form for the multi-GPU exchange: [nchains x 4 partials | 8 globals] = 4*nchains + 8 doubles.
+ * hb_accum_pack writes this rank's block to `dst` (HOST or DEVICE; device copies are asynchronous on
+ * `stream`): it is the send buffer of the one all-gather of the path.  hb_accum_merge_packed folds
+ * `nranks` such blocks (block r at packed + r*stride doubles, rank order = merge order) in one
+ * kernel launch. */
+int hb_accum_pack(hb_accum* acc, double* dst, int mem, void* stream);
+int hb_accum_merge_packed(hb_accum* acc, int nranks, const double* packed, int64_t stride, int mem,
+                          void* stream);
+
 /* Replaces Evidence.process_run (harmonic/evidence.py:125-189) and the shift selection
  * (harmonic/evidence.py:307-319): a single-CTA float64 kernel.  `shift_value_in` is the frozen
  * shift of an earlier call, or NaN to derive it from this call's scalars with `shift_mode`.
