@@ -9,9 +9,49 @@ cfg3: D=5 RealNVP 6+2 (examples/pima_indian.py:179-182), T = 0.9.
 cfg5: accumulation only, precomputed ln phi / ln posterior.
 Weights are seeded synthetic (no JAX in the image to train with).
 """
+import os
+
 import numpy as np
 
-from tests import util
+import harmonic_b200 as hm
+from harmonic_b200 import export
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def make_realnvp(ndim, n_scaled=2, n_unscaled=4, seed=0, standardize=False, temperature=0.8, ws=1.0):
+    """RealNVPModel with seeded synthetic weights (flax naming) installed through load_params."""
+    m = hm.model.RealNVPModel(ndim, n_scaled, n_unscaled, standardize=standardize, temperature=temperature)
+    rng = np.random.default_rng(seed + 1000)
+    off = rng.standard_normal(ndim).astype(np.float32) * 0.3 if standardize else None
+    amp = (0.5 + rng.random(ndim)).astype(np.float32) if standardize else None
+    m.load_params(export.random_realnvp_params(ndim, n_scaled, n_unscaled, seed=seed, weight_scale=ws), off, amp)
+    return m
+
+
+def make_rqspline(ndim, n_layers=3, n_bins=8, hidden=(32, 32), seed=0, standardize=False,
+                  temperature=0.9, spline_range=(-10.0, 10.0), ws=1.0):
+    m = hm.model.RQSplineModel(ndim, n_layers, n_bins, list(hidden), spline_range,
+                               standardize=standardize, temperature=temperature)
+    rng = np.random.default_rng(seed + 2000)
+    off = rng.standard_normal(ndim).astype(np.float32) * 0.3 if standardize else None
+    amp = (0.5 + rng.random(ndim)).astype(np.float32) if standardize else None
+    m.load_params(export.random_rqspline_params(ndim, n_layers, n_bins, hidden, seed=seed, weight_scale=ws), off, amp)
+    return m
+
+
+def load_cfg1_model(temperature=0.8):
+    """The trained cfg1 fixture (tests/golden/make_cfg1_flow.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cfg1_realnvp_flow.npz"))
+    params = {}
+    for k in z.files:
+        if "/" not in k:
+            continue
+        layer, dense, leaf = k.split("/")
+        params.setdefault(layer, {}).setdefault(dense, {})[leaf] = z[k]
+    m = hm.model.RealNVPModel(5, 2, 4, standardize=True, temperature=temperature)
+    m.load_params(params, z["pre_offset"], z["pre_amp"])
+    return m
 
 FLOP_PER_SAMPLE = {"cfg4": 114688.0, "cfg3": 14848.0, "cfg1": 9216.0, "cfg2": 118848.0}
 BYTES_PER_SAMPLE = {"cfg4": 260.0, "cfg3": 24.0, "cfg1": 24.0, "cfg2": 12.0, "cfg5": 8.0}
@@ -29,14 +69,13 @@ def init_cov(ndim, seed=10):
 
 def make_model(name):
     if name == "cfg4":
-        return util.make_realnvp(64, 2, 4, seed=4, standardize=True, temperature=0.8, ws=0.3)
+        return make_realnvp(64, 2, 4, seed=4, standardize=True, temperature=0.8, ws=0.3)
     if name == "cfg3":
-        return util.make_realnvp(5, 6, 2, seed=3, standardize=True, temperature=0.9, ws=0.3)
-    if name == "cfg1":  # the trained fixture (tests/golden/make_cfg1_flow.py)
-        from tests.test_cfg1_e2e import load_cfg1_model
+        return make_realnvp(5, 6, 2, seed=3, standardize=True, temperature=0.9, ws=0.3)
+    if name == "cfg1":
         return load_cfg1_model(0.8)
     if name == "cfg2":
-        return util.make_rqspline(2, 8, 8, (64, 64), seed=2, standardize=False, temperature=0.9, ws=0.15)
+        return make_rqspline(2, 8, 8, (64, 64), seed=2, standardize=False, temperature=0.9, ws=0.15)
     raise ValueError(name)
 
 

@@ -4,29 +4,14 @@ learned RealNVP flow at T = 0.8 -> ln Z against the ANALYTIC evidence.
 
 The flow weights are a committed fixture trained by tests/golden/make_cfg1_flow.py (torch stand-in
 for the reference's JAX training; jax is not installable here)."""
-import os
-
 import numpy as np
 import pytest
 
 import bench_workloads as wl
+from bench_workloads import load_cfg1_model
 import harmonic_b200 as hm
 from tests import util
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-
-
-def load_cfg1_model(temperature=0.8):
-    z = np.load(os.path.join(HERE, "golden", "cfg1_realnvp_flow.npz"))
-    params = {}
-    for k in z.files:
-        if "/" not in k:
-            continue
-        layer, dense, leaf = k.split("/")
-        params.setdefault(layer, {}).setdefault(dense, {})[leaf] = z[k]
-    m = hm.model.RealNVPModel(5, 2, 4, standardize=True, temperature=temperature)
-    m.load_params(params, z["pre_offset"], z["pre_amp"])
-    return m
 
 
 def cfg1_chains():

@@ -1,29 +1,9 @@
 import numpy as np
 
 import harmonic_b200 as hm
-from harmonic_b200 import export
+from bench_workloads import load_cfg1_model, make_realnvp, make_rqspline  # noqa: F401  (re-exported)
 from oracle import evidence as oe
 from oracle import flows as of
-
-
-def make_realnvp(ndim, n_scaled=2, n_unscaled=4, seed=0, standardize=False, temperature=0.8, ws=1.0):
-    m = hm.model.RealNVPModel(ndim, n_scaled, n_unscaled, standardize=standardize, temperature=temperature)
-    rng = np.random.default_rng(seed + 1000)
-    off = rng.standard_normal(ndim).astype(np.float32) * 0.3 if standardize else None
-    amp = (0.5 + rng.random(ndim)).astype(np.float32) if standardize else None
-    m.load_params(export.random_realnvp_params(ndim, n_scaled, n_unscaled, seed=seed, weight_scale=ws), off, amp)
-    return m
-
-
-def make_rqspline(ndim, n_layers=3, n_bins=8, hidden=(32, 32), seed=0, standardize=False,
-                  temperature=0.9, spline_range=(-10.0, 10.0), ws=1.0):
-    m = hm.model.RQSplineModel(ndim, n_layers, n_bins, list(hidden), spline_range,
-                               standardize=standardize, temperature=temperature)
-    rng = np.random.default_rng(seed + 2000)
-    off = rng.standard_normal(ndim).astype(np.float32) * 0.3 if standardize else None
-    amp = (0.5 + rng.random(ndim)).astype(np.float32) if standardize else None
-    m.load_params(export.random_rqspline_params(ndim, n_layers, n_bins, hidden, seed=seed, weight_scale=ws), off, amp)
-    return m
 
 
 def oracle_predict(model, x, dtype=np.float64):
