@@ -344,17 +344,22 @@ def main():
         ach = wl.BYTES_PER_SAMPLE[name] * n_local / (kms * 1e-3) / 1e9 if kms else None
         peak = float(peaks["hbm_gbs"])
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": (ach / peak) if ach else None, "traffic": None,
+                "frac": (ach / peak) if ach else None,
+                # ncu --set full (profiles/r1_prof_acc_r1_raw_summary.csv): dram read+write per sample
+                "traffic": 8.0053 * n_local, "traffic_unit": "bytes per launch (ncu dram bytes/sample x samples)",
                 "kernel": "accumulate_precomputed_kernel", "kernel_ms": kms,
                 "peak_source": "HBM copy bandwidth, of %s" % peak_kind}
     elif name == "cfg4" and args.path != "simt":
         ach = wl.FLOP_PER_SAMPLE[name] * n_local / (kms * 1e-3) / 1e12 if kms else None
         peak = float(peaks["bf16_tflops"]) / 2.0
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": (ach / peak) if ach else None, "traffic": None,
+                "frac": (ach / peak) if ach else None,
+                # ncu --set full (profiles/r1_prof_tc_r1f_raw_summary.csv): 263 B of DRAM traffic per sample
+                # (algorithmic 260 B): the kernel is not memory bound
+                "traffic": 263.0 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
                 "kernel": "realnvp_tc_kernel", "kernel_ms": kms,
                 "peak_source": "TF32 dense = bf16 burst / 2, of %s" % peak_kind,
-                "issued_mma_flop_factor": 3.0, "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
+                "issued_mma_flop_factor": 3.32, "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
     else:
         # small-ndim flows run on the FP32 CUDA cores (tensor tiles would be >= 75 % padding):
         # denominator = 148 SMs x 128 FMA lanes x 2 FLOP x max SM clock (nominal, not measured)
