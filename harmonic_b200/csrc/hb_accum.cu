@@ -558,6 +558,7 @@ int hb_accum_destroy(hb_accum* h) {
   cudaFree(acc->fin);
   for (int i = 0; i < 2; ++i) {
     if (acc->dev[i]) cudaFree(acc->dev[i]);
+    if (acc->pin[i]) cudaFreeHost(acc->pin[i]);
     if (acc->ev_copy[i]) cudaEventDestroy(acc->ev_copy[i]);
     if (acc->ev_done[i]) cudaEventDestroy(acc->ev_done[i]);
   }
@@ -604,6 +605,38 @@ int hb_accumulate_precomputed(hb_accum* h, const void* lnpred, int lnpred_dtype,
     return accumulate_precomputed_device(acc, lnpred, lnpred_dtype, ln_posterior, lp_dtype,
                                          start_indices, chain_lo, chain_hi, 0, nrows, st);
   // HOST buffers: chunked, double-buffered staging overlapped with the fold kernel
+  if (!is_pinned_host(lnpred) || !is_pinned_host(ln_posterior)) {
+    // pageable memory: host threads convert to float32 into pinned staging (see hb_accumulate_flow)
+    const long long chunkp = 1LL << 23;
+    const size_t offl = (size_t)chunkp * 4;
+    int rcp = ensure_stage(acc, 2 * offl);
+    if (rcp) return rcp;
+    rcp = ensure_pinned(acc, 2 * offl);
+    if (rcp) return rcp;
+    const int nth = host_threads();
+    int ip = 0;
+    for (long long a = 0; a < nrows; a += chunkp, ++ip) {
+      const long long b = (a + chunkp < nrows) ? a + chunkp : nrows;
+      const int sl = ip & 1;
+      char* hp = static_cast<char*>(acc->pin[sl]);
+      char* d = static_cast<char*>(acc->dev[sl]);
+      HB_CUDA(cudaEventSynchronize(acc->ev_copy[sl]));
+      if (lnpred_dtype == HB_F64) convert_rows((const double*)lnpred, 1, 1, a, b, (float*)hp, nth);
+      else convert_rows((const float*)lnpred, 1, 1, a, b, (float*)hp, nth);
+      if (lp_dtype == HB_F64) convert_rows((const double*)ln_posterior, 1, 1, a, b, (float*)(hp + offl), nth);
+      else convert_rows((const float*)ln_posterior, 1, 1, a, b, (float*)(hp + offl), nth);
+      HB_CUDA(cudaStreamWaitEvent(acc->copy_stream, acc->ev_done[sl], 0));
+      HB_CUDA(cudaMemcpyAsync(d, hp, offl + (size_t)(b - a) * 4, cudaMemcpyHostToDevice, acc->copy_stream));
+      HB_CUDA(cudaEventRecord(acc->ev_copy[sl], acc->copy_stream));
+      HB_CUDA(cudaStreamWaitEvent(st, acc->ev_copy[sl], 0));
+      rcp = accumulate_precomputed_device(acc, d, HB_F32, d + offl, HB_F32, start_indices, chain_lo, chain_hi,
+                                          a, b, st);
+      if (rcp) return rcp;
+      HB_CUDA(cudaEventRecord(acc->ev_done[sl], st));
+    }
+    HB_CUDA(cudaStreamSynchronize(st));
+    return HB_OK;
+  }
   const size_t es_p = lnpred_dtype == HB_F32 ? 4 : 8, es_l = lp_dtype == HB_F32 ? 4 : 8;
   const long long chunk = 1LL << 24;  // rows per chunk
   int rc = ensure_stage(acc, (size_t)chunk * (es_p + es_l));

@@ -313,6 +313,7 @@ struct Accum {
   void* pin[2] = {nullptr, nullptr};
   void* dev[2] = {nullptr, nullptr};
   size_t stage_cap = 0;
+  size_t pin_cap = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_done[2] = {nullptr, nullptr};

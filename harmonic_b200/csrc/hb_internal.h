@@ -1,5 +1,6 @@
 // Host-side internal declarations shared by the translation units of libharmonic_b200.
 #pragma once
+#include <thread>
 #include <vector>
 
 #include "hb_common.cuh"
@@ -8,6 +9,7 @@ namespace hb {
 
 int require_device(int device);
 int ensure_stage(Accum* acc, size_t bytes_per_slot);
+int ensure_pinned(Accum* acc, size_t bytes_per_slot);
 void timing_begin(cudaStream_t st);
 void timing_end(cudaStream_t st);
 
@@ -21,6 +23,47 @@ int reset_call_scalars(Accum* acc, cudaStream_t st);
 int accumulate_precomputed_device(Accum* acc, const void* lnpred, int pd, const void* lnpost, int ld,
                                   const int64_t* start, long long chain_lo, long long chain_hi,
                                   long long a, long long b, cudaStream_t st);
+
+// ---- host staging helpers --------------------------------------------------------------------
+inline bool is_pinned_host(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
+// rows [r0, r1) of a (n, ld) host matrix -> contiguous float32 (n, ncol), split across host threads
+template <typename T>
+inline void convert_rows(const T* src, long long ld, int ncol, long long r0, long long r1, float* dst,
+                         int nthreads) {
+  auto work = [=](long long a, long long b) {
+    for (long long r = a; r < b; ++r) {
+      const T* s = src + r * ld;
+      float* d = dst + (r - r0) * ncol;
+      for (int c = 0; c < ncol; ++c) d[c] = (float)s[c];
+    }
+  };
+  const long long n = r1 - r0;
+  if (nthreads <= 1 || n < 4096) {
+    work(r0, r1);
+    return;
+  }
+  std::vector<std::thread> th;
+  const long long per = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    const long long a = r0 + t * per, b = (a + per < r1) ? a + per : r1;
+    if (a >= b) break;
+    th.emplace_back(work, a, b);
+  }
+  for (auto& t : th) t.join();
+}
+
+inline int host_threads() {
+  int n = (int)std::thread::hardware_concurrency();
+  return n > 16 ? 16 : (n < 1 ? 1 : n);
+}
 
 // ---- flows -------------------------------------------------------------------------------
 struct RealNVPLayerDev {
