@@ -333,42 +333,53 @@ int hb_flow_predict(hb_flow* h, float temperature, const void* x, int x_dtype, i
   if (x_mem == HB_MEM_DEVICE && out_mem == HB_MEM_DEVICE)
     return flow_run(f, temperature, x, x_dtype, ld, n, nullptr, HB_F32, out, nullptr, nullptr, 0, 0,
                     0, n, st);
-  // host staging (simple, synchronous per chunk: predict-only is not the hot path)
+  // host staging (synchronous per chunk: predict-only is not the hot path).  Large pageable inputs are
+  // converted to float32 by host threads into a pinned buffer first (see hb_accumulate_flow).
   const size_t es = x_dtype == HB_F32 ? 4 : 8;
-  const long long chunk = 1LL << 20;
+  const int D = f->desc.ndim;
+  const bool threaded = x_mem == HB_MEM_HOST && n >= 65536 && !is_pinned_host(x);
+  const long long chunk = threaded ? (long long)((64ull << 20) / ((size_t)D * 4)) : (1LL << 20);
   void* dx = nullptr;
+  void* hpin = nullptr;
   float* dout = nullptr;
   const long long cap = n < chunk ? n : chunk;
-  if (x_mem == HB_MEM_HOST) HB_CUDA(cudaMalloc(&dx, (size_t)cap * ld * es));
-  if (out_mem == HB_MEM_HOST) {
-    cudaError_t e = cudaMalloc(&dout, (size_t)cap * sizeof(float));
-    if (e != cudaSuccess) {
-      if (dx) cudaFree(dx);
-      return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
-    }
-  }
   int rc = HB_OK;
+  cudaError_t e = cudaSuccess;
+  if (x_mem == HB_MEM_HOST) e = cudaMalloc(&dx, (size_t)cap * (threaded ? (size_t)D * 4 : (size_t)ld * es));
+  if (e == cudaSuccess && threaded) e = cudaHostAlloc(&hpin, (size_t)cap * D * 4, cudaHostAllocDefault);
+  if (e == cudaSuccess && out_mem == HB_MEM_HOST) e = cudaMalloc(&dout, (size_t)cap * sizeof(float));
+  if (e != cudaSuccess) rc = cuda_fail(e, "staging allocation", __FILE__, __LINE__);
+  const int nthreads = host_threads();
   for (long long a = 0; a < n && rc == HB_OK; a += chunk) {
     const long long b = (a + chunk < n) ? a + chunk : n;
     const void* xin = (const char*)x + (size_t)a * ld * es;
-    if (x_mem == HB_MEM_HOST) {
-      cudaError_t e = cudaMemcpyAsync(dx, xin, (size_t)(b - a) * ld * es, cudaMemcpyHostToDevice, st);
+    int xdt = x_dtype;
+    long long xld = ld;
+    if (threaded) {
+      if (x_dtype == HB_F64) convert_rows((const double*)x, ld, D, a, b, (float*)hpin, nthreads);
+      else convert_rows((const float*)x, ld, D, a, b, (float*)hpin, nthreads);
+      e = cudaMemcpyAsync(dx, hpin, (size_t)(b - a) * D * 4, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "H2D", __FILE__, __LINE__); break; }
+      xin = dx;
+      xdt = HB_F32;
+      xld = D;
+    } else if (x_mem == HB_MEM_HOST) {
+      e = cudaMemcpyAsync(dx, xin, (size_t)(b - a) * ld * es, cudaMemcpyHostToDevice, st);
       if (e != cudaSuccess) { rc = cuda_fail(e, "H2D", __FILE__, __LINE__); break; }
       xin = dx;
     }
     float* o = (out_mem == HB_MEM_HOST) ? dout : out + a;
-    rc = flow_run(f, temperature, xin, x_dtype, ld, b - a, nullptr, HB_F32, o, nullptr, nullptr, 0, 0,
-                  0, b - a, st);
+    rc = flow_run(f, temperature, xin, xdt, xld, b - a, nullptr, HB_F32, o, nullptr, nullptr, 0, 0, 0, b - a, st);
     if (rc) break;
     if (out_mem == HB_MEM_HOST) {
-      cudaError_t e = cudaMemcpyAsync(out + a, dout, (size_t)(b - a) * sizeof(float),
-                                      cudaMemcpyDeviceToHost, st);
+      e = cudaMemcpyAsync(out + a, dout, (size_t)(b - a) * sizeof(float), cudaMemcpyDeviceToHost, st);
       if (e != cudaSuccess) { rc = cuda_fail(e, "D2H", __FILE__, __LINE__); break; }
     }
-    cudaError_t e = cudaStreamSynchronize(st);
+    e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { rc = cuda_fail(e, "sync", __FILE__, __LINE__); break; }
   }
   if (dx) cudaFree(dx);
+  if (hpin) cudaFreeHost(hpin);
   if (dout) cudaFree(dout);
   return rc;
 }
