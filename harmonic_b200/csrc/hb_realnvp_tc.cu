@@ -4,11 +4,12 @@
 // + harmonic/evidence.py:278-352 for the shapes the tensor path supports (ndim = 64, <= 8 coupling
 // layers; everything else runs on the CUDA-core kernels).
 //
-// Mapping.  One persistent CTA per SM, 320 threads:
+// Mapping.  One persistent CTA per SM, 352 threads:
 //   warps 0-3 / 4-7 : two epilogue warpgroups; each owns one 128-sample tile at a time, one sample
 //                     per thread (TMEM lane = sample), y[64] in registers through all layers
-//   warp 8          : weight producer: streams the pre-split weight image (hi/lo TF32, UMMA canonical
-//                     no-swizzle K-major layout, built once on the host) from L2 into an 8-slot ring
+//   warp 8          : weight producer: streams the pre-split weight image (TF32 hi + FP16 correction
+//                     blocks, UMMA canonical no-swizzle K-major layout, built once on the host) from L2
+//                     into an 8-slot ring
 //                     of 16 KiB chunks with cp.async.bulk + mbarrier
 //   warps 9, 10     : tcgen05.mma issuers, one per tile (warp 9 also allocates TMEM); warp-uniform
 //                     straight-line program with blocking mbarrier waits, one elected lane issues
@@ -18,8 +19,16 @@
 //   E1     h = leaky_relu(H), split hi/lo, back to TMEM          four 32-column quarters
 //   GEMM2  O[128xN2] += h[:, quarter] . [Wt|Ws][quarter, :]      A from TMEM, one K = 32 step per quarter
 //   E2     shift / softplus-clip scale epilogue on y1, log-det
-// Each GEMM is 3xTF32: a.w ~= a_lo.w_hi + a_hi.w_lo + a_hi.w_hi with FP32 accumulation in TMEM
-// (hi = top 19 bits, lo = exact remainder), so per-sample ln phi keeps ~FP32 accuracy.
+// Split-precision contraction with FP32 accumulation in TMEM: a.w ~= a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo),
+// hi = top 19 bits (a TF32 value), lo = exact remainder.  The main term a_hi.w_hi runs as kind::tf32;
+// the two correction terms only need ~11 significant bits per factor, so they run as ONE kind::f16
+// contraction over the concatenated K' = [a_lo | a_hi] . [w_hi ; w_lo] (an 11-bit TF32 significand is
+// exactly an FP16 significand).  The hi half of the FP16 operand is stored * 2^-11 and w_lo * 2^11, so
+// all four FP16 factors sit at the magnitude of a_lo / w_hi: normal halves for |a| in ~[0.1, 1.3e8];
+// below that the loss is an absolute 3e-8 |w| per product, above it satfinite conversion clamps and the
+// result degrades to plain TF32 accuracy instead of inf/NaN.  Same ~2^-22 product accuracy as a 3xTF32
+// split at 2/3 of the MMA count and operand traffic.  What remains against a float32 FMA chain is the
+// tensor cores' truncating accumulator (profiles/r1_tensor_accum_rounding.txt), see DESIGN.md 4.1.
 //
 // GEMM1 without re-staging activations.  The flow permutes by one position per layer
 // (harmonic/flows.py:65-66), so layer l conditions on ORIGINAL features l .. l+31: the features below
@@ -32,8 +41,8 @@
 //
 // GEMM2 is pipelined with E1 at quarter granularity: quarter q of h_lo goes to Q buffer q & 1, its
 // GEMM2 step runs while the epilogue computes quarter q + 1.
-// TMEM (512 columns), per tile t at column 256 t:  P (128: H, then h_hi in place) | Q (2 x 32: h_lo
-// quarters) | O (64: GEMM2 accumulators).
+// TMEM (512 columns), per tile t at column 256 t:  P (128: H, then h_hi in place) | Q (2 x 32: packed
+// FP16 [h_lo | h_hi] quarters) | O (64: GEMM2 accumulators).
 #include <math.h>
 #include <string.h>
 
@@ -153,6 +162,35 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, u
       "}\n" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// {upper 16 bits: fp16(hi_elem), lower 16 bits: fp16(lo_elem)}, round to nearest, saturating
+__device__ __forceinline__ uint32_t pack_f16x2(float hi_elem, float lo_elem) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+__device__ __forceinline__ uint16_t to_f16(float v) {
+  uint16_t d;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(d) : "f"(v));
+  return d;
+}
 #define HB_R32(v, o)                                                                                  \
   "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),     \
       "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), \
@@ -202,6 +240,10 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  // c=F32 (1<<4), a=b=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -244,13 +286,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// clip(softplus(a), 1e-3, 1e3) with MUFU ex2/lg2 (harmonic/flows.py:177).  t = exp(-|a|) in (0, 1];
-// log1p(t) by a 4-term series below 0.06 (rel. err < 3e-6) and ln2 * lg2(1 + t) above.
+// clip(softplus(a), 1e-3, 1e3) (harmonic/flows.py:177).  t = exp(-|a|) in (0, 1] by MUFU ex2;
+// log1p(t) = 2 atanh(u), u = t / (2 + t) in (0, 1/3], as u times a degree-4 minimax polynomial in u^2
+// (relative error 8e-9): for a < 0 the scale IS log1p(t), so it has to be accurate in relative terms.
 __device__ __forceinline__ float softplus_clip_fast(float a) {
   const float t = ex2_approx(-1.4426950408889634f * fabsf(a));
-  const float series = t * fmaf(t, fmaf(t, fmaf(t, -0.25f, 0.33333334f), -0.5f), 1.0f);
-  const float via_log = 0.6931471805599453f * lg2_approx(1.0f + t);
-  const float sp = fmaxf(a, 0.f) + ((t < 0.06f) ? series : via_log);
+  const float u = t * rcp_approx(2.0f + t);
+  const float z = u * u;
+  const float p = fmaf(z, fmaf(z, fmaf(z, fmaf(z, 0.14087678f, 0.13980642f), 0.20012431f), 0.33333158f), 1.0f);
+  const float sp = fmaf(u + u, p, fmaxf(a, 0.f));
   return fminf(fmaxf(sp, 1e-3f), 1e3f);  // NaN in -> NaN out is handled by the caller's y1 path
 }
 
@@ -288,16 +332,25 @@ __device__ __forceinline__ void load_row<double>(const double* __restrict__ x, l
   }
 }
 
-// E1 for one 32-column quarter: h = leaky_relu(H) -> hi (top 19 bits) / lo (exact remainder).
+// The hi half of the FP16 correction operand is stored as a_hi * 2^-11 and meets w_lo * 2^11: both factors
+// then sit at the magnitude of a_lo / w_hi, well inside the normal half range (unscaled, w_lo of a typical
+// 0.03 weight is a subnormal half and costs ~1e-6 relative per product).
+constexpr float HI_SCALE = 4.8828125e-4f;
+
+// E1 for one 32-column quarter: h = leaky_relu(H) -> v: hi (top 19 bits, TF32), w: the kind::f16
+// correction operand, 16 words of packed lo pairs then 16 words of packed hi pairs (K' = [lo | hi]).
 // The bias b0 is already inside H (constant-one column of the A operand).
 __device__ __forceinline__ void e1_quarter(uint32_t (&v)[32], uint32_t (&w)[32]) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float h = __uint_as_float(v[j]);
-    h = fmaxf(h, 0.01f * h);
-    const uint32_t hb = __float_as_uint(h) & 0xffffe000u;
-    v[j] = hb;
-    w[j] = __float_as_uint(h - __uint_as_float(hb));
+  for (int jj = 0; jj < 16; ++jj) {
+    float h0 = __uint_as_float(v[2 * jj]), h1 = __uint_as_float(v[2 * jj + 1]);
+    h0 = fmaxf(h0, 0.01f * h0);
+    h1 = fmaxf(h1, 0.01f * h1);
+    const uint32_t b0 = __float_as_uint(h0) & 0xffffe000u, b1 = __float_as_uint(h1) & 0xffffe000u;
+    v[2 * jj] = b0;
+    v[2 * jj + 1] = b1;
+    w[jj] = pack_f16x2(h1 - __uint_as_float(b1), h0 - __uint_as_float(b0));
+    w[16 + jj] = pack_f16x2(__uint_as_float(b1) * HI_SCALE, __uint_as_float(b0) * HI_SCALE);
   }
 }
 
@@ -376,10 +429,12 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     const int t = warp - 9;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
     const uint32_t id128 = make_idesc(128), id64 = make_idesc(64), id32 = make_idesc(32);
-    const uint32_t a_x = sbase + SM_A1 + t * A_TILE;           // raw features, K-chunks 0..7
-    const uint32_t a_new = a_x + 8 * 2048;                      // new columns + constant one
-    const uint64_t adx_hi = make_desc(a_x, 2048, 128), adx_lo = make_desc(a_x + A_HALF, 2048, 128);
-    const uint64_t adn_hi = make_desc(a_new, 2048, 128), adn_lo = make_desc(a_new + A_HALF, 2048, 128);
+    const uint32_t ih128 = make_idesc_f16(128), ih64 = make_idesc_f16(64), ih32 = make_idesc_f16(32);
+    const uint32_t a_x = sbase + SM_A1 + t * A_TILE;           // TF32 block: raw features, K-chunks 0..7
+    const uint32_t a_new = a_x + 8 * 2048;                      // TF32 block: new columns + constant one
+    const uint32_t a_h = a_x + A_HALF;                          // FP16 block: lo raw 0-3 | hi raw 4-7 | lo new 8 | hi new 9
+    const uint64_t adx_hi = make_desc(a_x, 2048, 128), adx_f16 = make_desc(a_h, 2048, 128);
+    const uint64_t adn_hi = make_desc(a_new, 2048, 128), adn_f16 = make_desc(a_h + 8 * 2048, 2048, 128);
     auto wwait = [&](uint32_t gidx) {
       mbar_wait(BAR(B_WFULL + (gidx & (NSLOTS - 1))), (gidx / NSLOTS) & 1);
     };
@@ -388,25 +443,20 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       if (elect_one()) tc_commit(BAR(B_WEMPTY + (gidx & (NSLOTS - 1))));
       __syncwarp();
     };
-    // main part of GEMM1 (layer chunks g, g+1): H = x(0..31) . W0main, K = 32
+    // main part of GEMM1: H = x(0..31) . W0main.  Chunk g+1 = FP16 correction operand [128 x 64 K'],
+    // chunk g = TF32 hi operand [128 x 32]; corrections first (small terms), then the main term.
     auto issue_main = [&](uint32_t g) {
       wwait(g);
       wwait(g + 1);
       tc_fence_after();
-      const uint64_t w01 = make_desc(chunk_addr(g), 2048, 128), w23 = make_desc(chunk_addr(g + 1), 2048, 128);
+      const uint64_t wt = make_desc(chunk_addr(g), 2048, 128), wh = make_desc(chunk_addr(g + 1), 2048, 128);
       if (elect_one()) {
-        uint32_t acc = 0;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint64_t aa = (pass == 0) ? adx_lo : adx_hi;
-          const uint64_t boff = (pass == 1) ? (uint64_t)(8192 >> 4) : 0;  // lo block of the chunk
+        for (int k = 0; k < 4; ++k)
+          mma_ss_f16(tb + TM_P, adx_f16 + (uint64_t)(k * 256), wh + (uint64_t)(k * 256), ih128, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t bb = ((k < 2) ? w01 : w23) + boff + (uint64_t)((k & 1) * 256);
-            mma_ss(tb + TM_P, aa + (uint64_t)(k * 256), bb, id128, acc);
-            acc = 1;
-          }
-        }
+        for (int k = 0; k < 4; ++k)
+          mma_ss(tb + TM_P, adx_hi + (uint64_t)(k * 256), wt + (uint64_t)(k * 256), id128, 1);
       }
       __syncwarp();
     };
@@ -423,9 +473,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         {
           const uint64_t wc = make_desc(chunk_addr(g + 2), 2048, 128);
           if (elect_one()) {
-            mma_ss(tb + TM_P, adn_lo, wc, id128, 1);
-            mma_ss(tb + TM_P, adn_hi, wc + (uint64_t)(4096 >> 4), id128, 1);
-            mma_ss(tb + TM_P, adn_hi, wc, id128, 1);
+            mma_ss_f16(tb + TM_P, adn_f16, wc + (uint64_t)(4096 >> 4), ih128, 1);  // K' = 16: [lo new | hi new]
+            mma_ss(tb + TM_P, adn_hi, wc, id128, 1);                               // K = 8 TF32
             tc_commit(BAR(B_HFULL + t));
             tc_commit(BAR(B_WEMPTY + (g & (NSLOTS - 1))));
             tc_commit(BAR(B_WEMPTY + ((g + 1) & (NSLOTS - 1))));
@@ -438,7 +487,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         const uint32_t lbo2 = n2 * 16u;
         const uint32_t qbytes = 8 * lbo2;  // one quarter of hi (or lo): 8 K-chunks
         const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
-        const uint32_t id2 = scaled ? id64 : id32;
+        const uint32_t id2 = scaled ? id64 : id32, ih2 = scaled ? ih64 : ih32;
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           const uint32_t gw = g + 3 + (scaled ? q : (q >> 1));
@@ -446,20 +495,15 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           wwait(gw);
           tc_fence_after();
           const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? 2 * qbytes : 0);
-          const uint64_t bd_hi = make_desc(wbase, lbo2, 128), bd_lo = make_desc(wbase + qbytes, lbo2, 128);
-          const uint32_t a_lo = tb + TM_Q + 32 * (q & 1), a_hi = tb + TM_P + 32 * q;
+          // quarter block in the chunk: TF32 hi [N2 x 32] | FP16 [N2 x 64 K'] (same byte size)
+          const uint64_t bd_hi = make_desc(wbase, lbo2, 128), bd_f16 = make_desc(wbase + qbytes, lbo2, 128);
+          const uint32_t a_f16 = tb + TM_Q + 32 * (q & 1), a_hi = tb + TM_P + 32 * q;
           if (elect_one()) {
-            uint32_t acc = q ? 1u : 0u;
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t aa = (pass == 0) ? a_lo : a_hi;
-              const uint64_t bb = (pass == 1) ? bd_lo : bd_hi;
+            for (int k = 0; k < 4; ++k)
+              mma_ts_f16(tb + TM_O, a_f16 + k * 8, bd_f16 + (uint64_t)k * kstep2, ih2, (q | k) ? 1u : 0u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                mma_ts(tb + TM_O, aa + k * 8, bb + (uint64_t)k * kstep2, id2, acc);
-                acc = 1;
-              }
-            }
+            for (int k = 0; k < 4; ++k) mma_ts(tb + TM_O, a_hi + k * 8, bd_hi + (uint64_t)k * kstep2, id2, 1);
             tc_commit(BAR(B_QFREE + 2 * (q & 1) + t));
             if (q == 3) tc_commit(BAR(B_OFULL + t));
             if (scaled || (q & 1)) tc_commit(BAR(B_WEMPTY + (gw & (NSLOTS - 1))));
@@ -510,29 +554,37 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       }
 #pragma unroll
       for (int i = 0; i < D; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
-      // ---- A operand, written once per tile: raw features 0..31 (hi | lo), zeroed new columns,
-      // constant one in column 39.  (GEMM1 of the previous tile has completed: its HFULL was waited.)
+      // ---- A operand, written once per tile.  TF32 block: hi of raw features 0..31 (K-chunks 0-7),
+      // zeroed new columns and a constant one in column 39 (K-chunks 8, 9).  FP16 block (8 values per
+      // 16-byte chunk): lo of raw 0..31 (chunks 0-3), hi of raw (4-7), lo of new (8), hi of new (9).
+      // (GEMM1 of the previous tile has completed: its HFULL was waited.)
 #pragma unroll
-      for (int c = 0; c < DH / 4; ++c) {
-        uint4 hi, lo;
-        uint32_t* ph = &hi.x;
-        uint32_t* pl = &lo.x;
+      for (int c = 0; c < DH / 8; ++c) {
+        uint4 hi0, hi1, plo, phi;
+        uint32_t* p0 = &hi0.x;
+        uint32_t* p1 = &hi1.x;
+        uint32_t* ql = &plo.x;
+        uint32_t* qh = &phi.x;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float v = y[4 * c + q];
-          const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
-          ph[q] = hb;
-          pl[q] = __float_as_uint(v - __uint_as_float(hb));
+          const float va = y[8 * c + 2 * q], vb = y[8 * c + 2 * q + 1];
+          const uint32_t ha = __float_as_uint(va) & 0xffffe000u, hb = __float_as_uint(vb) & 0xffffe000u;
+          (q < 2 ? p0 : p1)[(2 * q) & 3] = ha;
+          (q < 2 ? p0 : p1)[(2 * q + 1) & 3] = hb;
+          ql[q] = pack_f16x2(vb - __uint_as_float(hb), va - __uint_as_float(ha));
+          qh[q] = pack_f16x2(__uint_as_float(hb) * HI_SCALE, __uint_as_float(ha) * HI_SCALE);
         }
-        *reinterpret_cast<uint4*>(a1 + c * 2048 + tid * 16) = hi;
-        *reinterpret_cast<uint4*>(a1 + A_HALF + c * 2048 + tid * 16) = lo;
+        *reinterpret_cast<uint4*>(a1 + (2 * c) * 2048 + tid * 16) = hi0;
+        *reinterpret_cast<uint4*>(a1 + (2 * c + 1) * 2048 + tid * 16) = hi1;
+        *reinterpret_cast<uint4*>(a1 + A_HALF + c * 2048 + tid * 16) = plo;
+        *reinterpret_cast<uint4*>(a1 + A_HALF + (4 + c) * 2048 + tid * 16) = phi;
       }
       {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = z;
         *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x3f800000u);
         *reinterpret_cast<uint4*>(a1 + A_HALF + 8 * 2048 + tid * 16) = z;
-        *reinterpret_cast<uint4*>(a1 + A_HALF + 9 * 2048 + tid * 16) = z;
+        *reinterpret_cast<uint4*>(a1 + A_HALF + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x10000000u);
       }
       float ldj = 0.f;
       for (int l = 0; l < nl; ++l, ++it) {
@@ -598,9 +650,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           const float v = y[DH];
           const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
           const int col = DH + l;
-          uint8_t* dst = a1 + (col >> 2) * 2048 + tid * 16 + (col & 3) * 4;
-          *reinterpret_cast<uint32_t*>(dst) = hb;
-          *reinterpret_cast<uint32_t*>(dst + A_HALF) = __float_as_uint(v - __uint_as_float(hb));
+          *reinterpret_cast<uint32_t*>(a1 + (col >> 2) * 2048 + tid * 16 + (col & 3) * 4) = hb;
+          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 8 * 2048 + tid * 16 + l * 2) = to_f16(v - __uint_as_float(hb));
+          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 9 * 2048 + tid * 16 + l * 2) = to_f16(__uint_as_float(hb) * HI_SCALE);
           // inverse of tfb.Permute([D-1, 0, .., D-2]): rotate left by one (flows.py:65-66)
           const float y0 = y[0];
 #pragma unroll
@@ -653,6 +705,48 @@ static inline void split_tf32(float v, float* hi, float* lo) {
 static inline size_t kmajor_off(int N, int n, int k) {
   return (size_t)(n / 8) * 32 + (size_t)(n % 8) * 4 + (size_t)(k / 4) * (N * 4) + (k % 4);
 }
+// same for a 16-bit operand (8 elements per 16-byte chunk), in halves
+static inline size_t kmajor_off16(int N, int n, int k) {
+  return (size_t)(n / 8) * 64 + (size_t)(n % 8) * 8 + (size_t)(k / 8) * (N * 8) + (k % 8);
+}
+
+// float -> IEEE half, round to nearest even, saturating to +-65504 (NaN stays NaN)
+static inline uint16_t f32_to_f16(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const uint32_t absx = x & 0x7fffffffu;
+  if (absx > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);
+  if (absx >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);  // >= 65520 rounds past the largest half
+  if (absx < 0x33000001u) return (uint16_t)sign;                // < 2^-25 (rounds to zero)
+  const int e = (int)(absx >> 23) - 127;
+  uint32_t mant = (absx & 0x7fffffu) | 0x800000u;
+  if (e < -14) {  // subnormal half: value = mant * 2^(e-23), unit = 2^-24
+    const int shift = -e - 1;  // 13 + (-14 - e)
+    const uint32_t q = mant >> shift, rem = mant & ((1u << shift) - 1), half = 1u << (shift - 1);
+    uint32_t r = q;
+    if (rem > half || (rem == half && (q & 1))) ++r;
+    return (uint16_t)(sign | r);
+  }
+  uint32_t q = mant >> 13, rem = mant & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (q & 1))) ++q;
+  uint32_t he = (uint32_t)(e + 15);
+  if (q & 0x800u) {  // mantissa overflowed to 2.0
+    q >>= 1;
+    ++he;
+  }
+  return (uint16_t)(sign | (he << 10) | (q & 0x3ffu));
+}
+
+// one weight w into the TF32 main operand (hi) and the FP16 correction operand: row kh holds fp16(hi)
+// (meets a_lo), row kl holds fp16(lo) (meets a_hi)
+static inline void put_weight(float w, float* t32, size_t off32, uint16_t* h16, size_t off_hi, size_t off_lo) {
+  float hi, lo;
+  split_tf32(w, &hi, &lo);
+  t32[off32] = hi;
+  h16[off_hi] = f32_to_f16(hi);
+  h16[off_lo] = f32_to_f16(lo * 2048.0f);  // 1 / HI_SCALE
+}
 
 int realnvp_tc_prepare(Flow* f) {
   f->tc_ok = false;
@@ -677,39 +771,40 @@ int realnvp_tc_prepare(Flow* f) {
     const float* Ws = bt + u;
     const float* bs = Ws + (size_t)128 * u;
     // GEMM1 main: A column i (original feature i < 32) meets W0 row i - l (zero for i < l).
-    // chunk 0: k = 0..15 (hi 8 KB | lo 8 KB), chunk 1: k = 16..31
-    for (int i = 0; i < 32; ++i) {
-      float* c = img.data() + (ch + (i >> 4)) * CF;
-      for (int n = 0; n < 128; ++n) {
-        const float v = (i >= l) ? W0[(size_t)(i - l) * 128 + n] : 0.f;
-        const size_t off = kmajor_off(128, n, i & 15);
-        split_tf32(v, &c[off], &c[2048 + off]);
-      }
+    // chunk 0: TF32 hi [128 x 32]; chunk 1: FP16 [128 x 64 K']: K' < 32 fp16(hi), K' >= 32 fp16(lo)
+    {
+      float* c0 = img.data() + ch * CF;
+      uint16_t* c1 = reinterpret_cast<uint16_t*>(img.data() + (ch + 1) * CF);
+      for (int i = 0; i < 32; ++i)
+        for (int n = 0; n < 128; ++n) {
+          const float v = (i >= l) ? W0[(size_t)(i - l) * 128 + n] : 0.f;
+          put_weight(v, c0, kmajor_off(128, n, i), c1, kmajor_off16(128, n, i), kmajor_off16(128, n, 32 + i));
+        }
     }
     // GEMM1 correction (chunk 2): k = 0..6 <-> frozen feature 32 + j meets W0 row 32 - l + j (j < l),
-    // k = 7 <-> constant one column carrying the bias b0.  hi 4 KB | lo 4 KB
+    // k = 7 <-> constant-one column carrying the bias b0.  TF32 hi [128 x 8] 4 KB | FP16 [128 x 16 K'] 4 KB
     {
       float* c = img.data() + (ch + 2) * CF;
+      uint16_t* ch16 = reinterpret_cast<uint16_t*>(c + 1024);
       for (int k = 0; k < 8; ++k)
         for (int n = 0; n < 128; ++n) {
           float v = 0.f;
           if (k == 7) v = b0[n];
           else if (k < l) v = W0[(size_t)(32 - l + k) * 128 + n];
-          const size_t off = kmajor_off(128, n, k);
-          split_tf32(v, &c[off], &c[1024 + off]);
+          put_weight(v, c, kmajor_off(128, n, k), ch16, kmajor_off16(128, n, k), kmajor_off16(128, n, 8 + k));
         }
     }
-    // GEMM2: B[n][k] = [Wt | Ws][k][n]; one K = 32 quarter = hi block | lo block
+    // GEMM2: B[n][k] = [Wt | Ws][k][n]; one K = 32 quarter = TF32 hi block | FP16 block [N2 x 64 K']
     const int N2 = scaled ? 64 : 32;
     const size_t qf = (size_t)8 * N2 * 4;  // floats per quarter block (8 K-chunks)
     for (int q = 0; q < 4; ++q) {
       float* c = scaled ? img.data() + (ch + 3 + q) * CF : img.data() + (ch + 3 + (q >> 1)) * CF + (q & 1) * 2 * qf;
+      uint16_t* c16 = reinterpret_cast<uint16_t*>(c + qf);
       for (int kk = 0; kk < 32; ++kk)
         for (int n = 0; n < N2; ++n) {
           const int k = 32 * q + kk;
           const float v = (n < u) ? Wt[(size_t)k * u + n] : Ws[(size_t)k * u + (n - u)];
-          const size_t off = kmajor_off(N2, n, kk);
-          split_tf32(v, &c[off], &c[qf + off]);
+          put_weight(v, c, kmajor_off(N2, n, kk), c16, kmajor_off16(N2, n, kk), kmajor_off16(N2, n, 32 + kk));
         }
     }
     ch += scaled ? 7 : 5;

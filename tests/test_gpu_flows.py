@@ -174,6 +174,28 @@ def test_realnvp_tcgen05_layers_nan(layers):
     assert np.isnan(got[11]) and np.isnan(got[12])
 
 
+@pytest.mark.parametrize("scale,mult", [(5.0, 1.0), (30.0, 8.0), (3e4, None)])
+def test_realnvp_tcgen05_large_magnitude(scale, mult):
+    """Inputs far outside the trained range: the scaled layers hit the 1e-3 clip, which multiplies every
+    float32 rounding error by up to 1e3 per layer.  The tensor-core path (TF32 hi + FP16 correction
+    operands, the hi half stored * 2^-11) must stay finite and inside the conditioning-aware bound of
+    check_predict.  Where the flow is this ill-conditioned the bound is widened 8x: the tensor cores
+    truncate their float32 accumulator on every MMA step (profiles/r1_tensor_accum_rounding.txt), about
+    3-6x the error of a float32 FMA chain over the 32 accumulation steps of one coupling layer."""
+    m = util.make_realnvp(64, seed=5, standardize=True, ws=0.3)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = (samples(4000, 64, seed=16) * scale).astype(np.float32)
+    got = m.predict(x)
+    assert np.isfinite(got).all()
+    if mult is None:
+        # activations beyond 65504 * 2^11 = 1.3e8 saturate the FP16 correction operands: the path degrades
+        # to plain TF32 accuracy (2^-11 per product) instead of failing; float32 itself is meaningless here
+        want = util.oracle_predict(m, x)
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-2
+    else:
+        util.check_predict(m, x, got, slack_mult=mult)
+
+
 def test_realnvp_tcgen05_fused_vs_oracle_and_auto_path():
     m = util.make_realnvp(64, seed=9, standardize=True, ws=0.3)
     lib = _lib.load()
