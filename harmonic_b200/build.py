@@ -12,7 +12,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-cudart", "static",
-]
+] + os.environ.get("HB_NVCC_EXTRA", "").split()  # e.g. -DHB_TC_TRACE for tools/tc_trace.py
 
 
 def _stale():

@@ -98,6 +98,20 @@ struct Params {
   int nbatches;           // tiles per warpgroup
 };
 
+// ---- optional phase trace (-DHB_TC_TRACE, development builds only; see tools/tc_trace.py) ----
+#ifdef HB_TC_TRACE
+constexpr int TRACE_LEN = 4096;
+__device__ unsigned long long g_trace[4][TRACE_LEN];
+__device__ int g_trace_n[4];
+#define TR(code)                                                                              \
+  do {                                                                                        \
+    if (tr_on && tr_n < TRACE_LEN)                                                            \
+      g_trace[tr_s][tr_n++] = ((unsigned long long)clock64() << 8) | (unsigned long long)(code); \
+  } while (0)
+#else
+#define TR(code)
+#endif
+
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -361,7 +375,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __restrict__ lnpost,
                   float* __restrict__ lnpred_out, FoldParams fp) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
+  // lane-0 broadcast: tells the compiler the warp index (and with it the role dispatch below) is
+  // warp-uniform, so the MMA warps' addresses, descriptors and loop state live on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SM_BAR;
@@ -370,6 +386,11 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS);
   float* pre_s = reinterpret_cast<float*>(smem + SM_PRE);
   const int nl = P.nlayers;
+#ifdef HB_TC_TRACE
+  int tr_n = 0;
+  const bool tr_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp >= 9);
+  const int tr_s = warp == 0 ? 0 : warp == 4 ? 1 : warp == 9 ? 2 : 3;
+#endif
 
   // ---- one-time setup -------------------------------------------------------------------
   if (threadIdx.x == 0) {
@@ -467,6 +488,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         const uint32_t par = it & 1;
         // ---- GEMM1: (main, unless issued early) + correction
         mbar_wait(BAR(B_A1FULL + t), par);
+        TR(20);
         if (l == 0) issue_main(g);
         wwait(g + 2);
         tc_fence_after();
@@ -481,6 +503,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             tc_commit(BAR(B_WEMPTY + ((g + 2) & (NSLOTS - 1))));
           }
           __syncwarp();
+          TR(21);
         }
         // ---- GEMM2: four K = 32 quarters, each as soon as its half of E1 has landed
         const uint32_t n2 = scaled ? 64u : 32u;
@@ -492,6 +515,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         for (int q = 0; q < 4; ++q) {
           const uint32_t gw = g + 3 + (scaled ? q : (q >> 1));
           mbar_wait(BAR(B_A2 + 2 * (q & 1) + t), (uint32_t)(q >> 1));
+          TR(22 + q);
           wwait(gw);
           tc_fence_after();
           const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? 2 * qbytes : 0);
@@ -509,13 +533,16 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             if (scaled || (q & 1)) tc_commit(BAR(B_WEMPTY + (gw & (NSLOTS - 1))));
           }
           __syncwarp();
+          TR(26 + q);
         }
         g += layer_chunks(scaled);
         // ---- early main part of the next layer: runs under this layer's E2.  P is GEMM2's A operand
         // until the last quarter has drained.
         if (l + 1 < nl) {
           mbar_wait(BAR(B_OFULL + t), par);
+          TR(30);
           issue_main(g);
+          TR(31);
         }
       }
     }
@@ -546,6 +573,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       const bool live = r < row_hi;
       const long long rr = live ? r : 0;
       float y[D];
+      TR(1);
       load_row<XT>(x, ld, rr, y);
       if (r + TILE < row_hi) {  // pull the next tile's row into L2 while this tile computes
         const char* nx = reinterpret_cast<const char*>(x + (r + TILE) * ld);
@@ -594,10 +622,12 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         fence_proxy_async();
         tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
         mbar_arrive(BAR(B_A1FULL + wg));
+        TR(2);
         // ---- E1: four quarters; quarter q's h_lo goes to Q buffer q & 1 and its GEMM2 step runs
         // while quarter q + 1 is computed
         mbar_wait(BAR(B_HFULL + wg), par);
         tc_fence_after();
+        TR(3);
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           uint32_t v[32], w[32];
@@ -613,10 +643,12 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(BAR(B_A2 + 2 * (q & 1) + wg));
+          TR(4 + q);
         }
         // ---- E2: y1 = (y1 - shift) / scale, ldj -= sum log scale
         mbar_wait(BAR(B_OFULL + wg), par);
         tc_fence_after();
+        TR(9);
         {
           uint32_t sh[32];
           tmem_ld32(tm_o, sh);
@@ -659,6 +691,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           for (int i = 0; i < D - 1; ++i) y[i] = y[i + 1];
           y[D - 1] = y0;
         }
+        TR(10);
       }
       float ss = 0.f;
 #pragma unroll
@@ -678,6 +711,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     }
     if (FOLD) fold.finish(had_rows);
   }
+#ifdef HB_TC_TRACE
+  if (tr_on) g_trace_n[tr_s] = tr_n;
+#endif
 
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before();
@@ -689,6 +725,14 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 }
 
 }  // namespace tc
+
+#ifdef HB_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int hb_debug_trace_read(unsigned long long* dst, int* n) {
+  if (cudaMemcpyFromSymbol(dst, tc::g_trace, sizeof(unsigned long long) * 4 * tc::TRACE_LEN) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(n, tc::g_trace_n, sizeof(int) * 4) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // host side: weight image (hi/lo split, canonical K-major no-swizzle layout, 16 KiB chunks)
