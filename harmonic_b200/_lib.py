@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libharmonic_b200.so")
+# HARMONIC_B200_LIB selects another build of the same library (kernel A/B measurements); always a CUDA build
+LIB_PATH = os.environ.get("HARMONIC_B200_LIB") or os.path.join(HERE, "libharmonic_b200.so")
 
 HB_FLOW_REALNVP, HB_FLOW_RQSPLINE = 1, 2
 HB_F32, HB_F64 = 0, 1

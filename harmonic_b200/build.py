@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libharmonic_b200.so")
+LIB = os.environ.get("HB_BUILD_OUT") or os.path.join(HERE, "libharmonic_b200.so")  # HB_BUILD_OUT: variant builds
 SOURCES = ["hb_api.cu", "hb_accum.cu", "hb_flow_simt.cu", "hb_realnvp_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -29,9 +29,10 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build" + os.environ.get("HB_BUILD_TAG", ""))
+    os.makedirs(bdir, exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)

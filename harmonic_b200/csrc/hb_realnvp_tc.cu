@@ -239,6 +239,35 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
   asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], " HB_LIST32_FROM1 ";" ::"r"(taddr), HB_W32(v, 0)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// wait::ld that also names the registers of the load it completes: a prefetched chunk's values cannot be
+// consumed (or moved by the compiler) ahead of the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -351,20 +380,20 @@ __device__ __forceinline__ void load_row<double>(const double* __restrict__ x, l
 // 0.03 weight is a subnormal half and costs ~1e-6 relative per product).
 constexpr float HI_SCALE = 4.8828125e-4f;
 
-// E1 for one 32-column quarter: h = leaky_relu(H) -> v: hi (top 19 bits, TF32), w: the kind::f16
-// correction operand, 16 words of packed lo pairs then 16 words of packed hi pairs (K' = [lo | hi]).
+// E1 for one 16-column chunk: h = leaky_relu(H) -> v: hi (top 19 bits, TF32) in place; wl / wh: the
+// kind::f16 correction operand, 8 words of packed lo pairs and 8 words of packed scaled hi pairs.
 // The bias b0 is already inside H (constant-one column of the A operand).
-__device__ __forceinline__ void e1_quarter(uint32_t (&v)[32], uint32_t (&w)[32]) {
+__device__ __forceinline__ void e1_chunk(uint32_t (&v)[16], uint32_t (&wl)[8], uint32_t (&wh)[8]) {
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj) {
+  for (int jj = 0; jj < 8; ++jj) {
     float h0 = __uint_as_float(v[2 * jj]), h1 = __uint_as_float(v[2 * jj + 1]);
     h0 = fmaxf(h0, 0.01f * h0);
     h1 = fmaxf(h1, 0.01f * h1);
     const uint32_t b0 = __float_as_uint(h0) & 0xffffe000u, b1 = __float_as_uint(h1) & 0xffffe000u;
     v[2 * jj] = b0;
     v[2 * jj + 1] = b1;
-    w[jj] = pack_f16x2(h1 - __uint_as_float(b1), h0 - __uint_as_float(b0));
-    w[16 + jj] = pack_f16x2(__uint_as_float(b1) * HI_SCALE, __uint_as_float(b0) * HI_SCALE);
+    wl[jj] = pack_f16x2(h1 - __uint_as_float(b1), h0 - __uint_as_float(b0));
+    wh[jj] = pack_f16x2(__uint_as_float(b1) * HI_SCALE, __uint_as_float(b0) * HI_SCALE);
   }
 }
 
@@ -623,27 +652,38 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
         mbar_arrive(BAR(B_A1FULL + wg));
         TR(2);
-        // ---- E1: four quarters; quarter q's h_lo goes to Q buffer q & 1 and its GEMM2 step runs
-        // while quarter q + 1 is computed
+        // ---- E1 in eight 16-column chunks, software pipelined: chunk c + 1 is in flight from TMEM while
+        // chunk c is computed.  Chunks 2q, 2q + 1 form quarter q: its FP16 operand goes to Q buffer q & 1 and
+        // its GEMM2 step runs under the following chunks.
         mbar_wait(BAR(B_HFULL + wg), par);
         tc_fence_after();
         TR(3);
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          uint32_t v[32], w[32];
-          tmem_ld32(tm_p + q * 32, v);
-          tmem_ld_wait();
-          e1_quarter(v, w);
-          tmem_st32(tm_p + q * 32, v);
-          if (q >= 2) {  // Q buffer q & 1 is still GEMM2 quarter q - 2's operand until then
-            mbar_wait(BAR(B_QFREE + 2 * (q & 1) + wg), 0);
-            tc_fence_after();
+        {
+          uint32_t va[16], vb[16];
+          tmem_ld16(tm_p, va);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t(&cur)[16] = (c & 1) ? vb : va;
+            uint32_t(&nxt)[16] = (c & 1) ? va : vb;
+            const int q = c >> 1;
+            tmem_ld_wait16(cur);
+            if (c < 7) tmem_ld16(tm_p + (c + 1) * 16, nxt);
+            uint32_t wl[8], wh[8];
+            e1_chunk(cur, wl, wh);
+            tmem_st16(tm_p + c * 16, cur);
+            if (c == 4 || c == 6) {  // Q buffer q & 1 is still GEMM2 quarter q - 2's operand until then
+              mbar_wait(BAR(B_QFREE + 2 * (q & 1) + wg), 0);
+              tc_fence_after();
+            }
+            tmem_st8(tm_q + (q & 1) * 32 + (c & 1) * 8, wl);
+            tmem_st8(tm_q + (q & 1) * 32 + 16 + (c & 1) * 8, wh);
+            if (c & 1) {
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(BAR(B_A2 + 2 * (q & 1) + wg));
+              TR(4 + q);
+            }
           }
-          tmem_st32(tm_q + (q & 1) * 32, w);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(BAR(B_A2 + 2 * (q & 1) + wg));
-          TR(4 + q);
         }
         // ---- E2: y1 = (y1 - shift) / scale, ldj -= sum log scale
         mbar_wait(BAR(B_OFULL + wg), par);
