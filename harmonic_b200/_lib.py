@@ -49,6 +49,8 @@ SIGNATURES = {
     "hb_flow_uses_tcgen05": (C.c_int, [C.c_void_p]),
     "hb_flow_predict": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                   C.c_void_p, C.c_int, C.c_void_p]),
+    "hb_flow_sample": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
+                                 C.c_int, C.c_void_p]),
     "hb_accum_create": (C.c_int, [C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     "hb_accum_destroy": (C.c_int, [C.c_void_p]),
     "hb_accum_reset": (C.c_int, [C.c_void_p]),

@@ -384,6 +384,46 @@ int hb_flow_predict(hb_flow* h, float temperature, const void* x, int x_dtype, i
   return rc;
 }
 
+int hb_flow_sample(hb_flow* h, float temperature, const void* eps, int eps_dtype, int64_t n, int64_t ld,
+                   float* out, int mem, void* stream) {
+  HB_REQUIRE(h != nullptr, "hb_flow_sample: NULL handle");
+  Flow* f = reinterpret_cast<Flow*>(h);
+  HB_REQUIRE(temperature <= 1.f, "Scaling must not be greater than 1.");
+  HB_REQUIRE(temperature > 0.f, "Scaling must be positive.");
+  HB_REQUIRE(n >= 0 && ld >= f->desc.ndim, "bad shape");
+  HB_REQUIRE(eps_dtype == HB_F32 || eps_dtype == HB_F64, "dtype must be HB_F32 or HB_F64");
+  if (n == 0) return HB_OK;
+  HB_REQUIRE(eps != nullptr && out != nullptr, "NULL buffer");
+  HB_CUDA(cudaSetDevice(f->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = f->desc.ndim;
+  if (mem == HB_MEM_DEVICE) return flow_sample_run(f, temperature, eps, eps_dtype, ld, n, out, D, st);
+  // host buffers: staged in chunks (sampling is a diagnostic path, not the hot one)
+  const size_t es = eps_dtype == HB_F32 ? 4 : 8;
+  const long long chunk = 1LL << 20;
+  const long long cap = n < chunk ? n : chunk;
+  void* de = nullptr;
+  float* dout = nullptr;
+  int rc = HB_OK;
+  cudaError_t e = cudaMalloc(&de, (size_t)cap * ld * es);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)cap * D * sizeof(float));
+  if (e != cudaSuccess) rc = cuda_fail(e, "staging allocation", __FILE__, __LINE__);
+  for (long long a = 0; a < n && rc == HB_OK; a += chunk) {
+    const long long b = (a + chunk < n) ? a + chunk : n;
+    e = cudaMemcpyAsync(de, (const char*)eps + (size_t)a * ld * es, (size_t)(b - a) * ld * es,
+                        cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "H2D", __FILE__, __LINE__); break; }
+    rc = flow_sample_run(f, temperature, de, eps_dtype, ld, b - a, dout, D, st);
+    if (rc) break;
+    e = cudaMemcpyAsync(out + (size_t)a * D, dout, (size_t)(b - a) * D * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "D2H", __FILE__, __LINE__); break; }
+  }
+  if (de) cudaFree(de);
+  if (dout) cudaFree(dout);
+  return rc;
+}
+
 int hb_accumulate_flow(hb_accum* ha, hb_flow* hf, float temperature, const void* x, int x_dtype,
                        int64_t ld, const void* ln_posterior, int lp_dtype, int mem,
                        const int64_t* start_indices, int64_t chain_lo, int64_t chain_hi,

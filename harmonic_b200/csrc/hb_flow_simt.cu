@@ -377,6 +377,66 @@ __device__ __forceinline__ void rqs_forward(float x, const float* ps, int tid, i
           2.f * logf(denominator);
 }
 
+// distrax.RationalQuadraticSpline inverse (quadratic root) for one scalar; params in a smem column.
+// Used by the sampling direction only (harmonic/flows.py:290-313).
+__device__ __forceinline__ float rqs_inverse(float y, const float* ps, int tid, int K, float lo, float hi) {
+  const float mbs = 1e-4f, mks = 1e-4f;
+  const float off = logf(expf(1.f - mks) - 1.f);
+  const float R = hi - lo;
+  const float span = R - (float)K * mbs;
+  if (y <= lo) {
+    const float s0 = softplus_acc(ps[(2 * K) * FT + tid] + off) + mks;
+    return (y - lo) / s0 + lo;
+  }
+  if (y >= hi) {
+    const float sK = softplus_acc(ps[(3 * K) * FT + tid] + off) + mks;
+    return (y - hi) / sK + hi;
+  }
+  float mw = -CUDART_INF_F, mh = -CUDART_INF_F;
+  for (int k = 0; k < K; ++k) {
+    mw = fmaxf(mw, ps[k * FT + tid]);
+    mh = fmaxf(mh, ps[(K + k) * FT + tid]);
+  }
+  float sw = 0.f, shh = 0.f;
+  for (int k = 0; k < K; ++k) {
+    sw += expf(ps[k * FT + tid] - mw);
+    shh += expf(ps[(K + k) * FT + tid] - mh);
+  }
+  float xl = lo, yl = lo, cw = 0.f, chh = 0.f;
+  float bxl = lo, bxr = lo, byl = lo, byr = lo;
+  int kb = -1;
+  for (int k = 0; k < K; ++k) {
+    const float w = expf(ps[k * FT + tid] - mw) / sw * span + mbs;
+    const float h = expf(ps[(K + k) * FT + tid] - mh) / shh * span + mbs;
+    cw += w;
+    chh += h;
+    const float xr = (k == K - 1) ? hi : lo + cw;
+    const float yr = (k == K - 1) ? hi : lo + chh;
+    if (k == 0) { bxl = xl; bxr = xr; byl = yl; byr = yr; }  // default bin 0 (e.g. NaN input)
+    if (kb < 0 && y >= yl && y < yr) {
+      kb = k; bxl = xl; bxr = xr; byl = yl; byr = yr;
+    }
+    xl = xr;
+    yl = yr;
+  }
+  if (kb < 0) kb = 0;
+  const float sl = softplus_acc(ps[(2 * K + kb) * FT + tid] + off) + mks;
+  const float sr = softplus_acc(ps[(2 * K + kb + 1) * FT + tid] + off) + mks;
+  const float bw = bxr - bxl, bh = byr - byl;
+  const float delta = bh / bw;
+  float w = (y - byl) / bh;
+  w = fminf(fmaxf(w, 0.f), 1.f);
+  if (isnan(y)) w = y;
+  const float slopes_term = sr + sl - 2.f * delta;
+  const float c = -delta * w;
+  const float b = sl - slopes_term * w;
+  const float a = delta - b;
+  float z = -2.f * c / (b + sqrtf(b * b - 4.f * a * c));
+  z = fminf(fmaxf(z, 0.f), 1.f);
+  if (isnan(y)) z = y;
+  return bw * z + bxl;
+}
+
 template <typename XT, typename LT, bool FOLD>
 __global__ void __launch_bounds__(FT)
 rqspline_simt_kernel(RQParams P, const XT* __restrict__ x, long long ld,
@@ -1214,16 +1274,10 @@ int rqspline_prepare(Flow* f) {
   return rqspline_fast_prepare(f);
 }
 
-int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
-                 const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
-                 const int64_t* start, long long chain_lo, long long chain_hi, long long a,
-                 long long b, cudaStream_t st) {
-  if (n <= 0) return HB_OK;
-  if (f->rqf_pack && !f->force_generic)
-    return rqspline_fast_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start, chain_lo,
-                             chain_hi, a, b, st);
+// kernel parameters of the generic RQSpline kernels (log_prob and sampling direction)
+static void rq_params(Flow* f, float T, RQParams* out) {
   const hb_flow_desc& ds = f->desc;
-  RQParams P;
+  RQParams& P = *out;
   P.pack = f->rq_pack;
   P.pre = ds.standardize ? f->dev_weights : nullptr;
   P.D = ds.ndim;
@@ -1247,6 +1301,18 @@ int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, lon
   P.T = T;
   P.sum_log_amp = f->sum_log_amp;
   P.layers = reinterpret_cast<const RQLayer*>(f->rq_pack + f->rq_off[0]);
+}
+
+int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                 const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                 const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                 long long b, cudaStream_t st) {
+  if (n <= 0) return HB_OK;
+  if (f->rqf_pack && !f->force_generic)
+    return rqspline_fast_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start, chain_lo,
+                             chain_hi, a, b, st);
+  RQParams P;
+  rq_params(f, T, &P);
   const size_t smem = ((size_t)P.D + 2 * (size_t)P.maxw + P.npar_pad) * FT * sizeof(float);
   if (smem > 227 * 1024) {
     set_error("RQSpline: ndim / hidden sizes too large for shared memory");
@@ -1274,6 +1340,181 @@ int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, lon
   count_launch();
   HB_CUDA(cudaGetLastError());
   if (acc) return launch_merge(acc, fp, chain_lo, nfl, st);
+  return HB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Sampling direction: FlowModel.sample (harmonic/model.py:239-275) with the standard-normal draws supplied
+// by the caller.  RealNVP (flows.py:118-138): tfb.Chain.forward applies [S0, P, S1, ..] right to left, a
+// coupling's forward is y1 = x1 * scale(x0) + shift(x0), base = T * eps.  RQSpline (flows.py:290-313):
+// Inverse(Chain).forward = the inverses of [affine_0, spline_0, affine_1, ..] in list order,
+// base = sqrt(T) * eps.  Same shared-memory layout and weight packs as the log_prob kernels above.
+// ------------------------------------------------------------------------------------------
+template <typename ET>
+__global__ void __launch_bounds__(FT)
+realnvp_sample_kernel(RealNVPSimtParams P, const ET* __restrict__ eps, long long ld,
+                      float* __restrict__ out, long long ldo, long long nrows) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int D = P.D, d = P.d, u = P.u;
+  float* ys = smem;
+  float* hs = ys + (size_t)D * FT;
+  float* os = hs + (size_t)128 * FT;
+  for (long long t0 = (long long)blockIdx.x * FT; t0 < nrows; t0 += (long long)gridDim.x * FT) {
+    const long long r = t0 + tid;
+    const bool live = r < nrows;
+    const long long rr = live ? r : t0;
+    {
+      const int rot = (P.nlayers - 1) % D;  // base space: logical i lives in physical row (i + L - 1) mod D
+      for (int i = 0; i < D; ++i) {
+        int k = i + rot;
+        if (k >= D) k -= D;
+        ys[k * FT + tid] = P.T * (float)eps[rr * ld + i];
+      }
+    }
+    for (int l = P.nlayers - 1; l >= 0; --l) {
+      const SimtLayer L = P.layers[l];
+      const int rot = l % D;
+      auto phys = [&](int i) { int k = i + rot; return k >= D ? k - D : k; };
+      auto all = [](int) { return true; };
+      dense_cols<2>(ys, phys, all, d, P.pack + L.w0, 128, P.pack + L.b0, 128, hs, tid);
+      dense_cols<0>(hs, [](int i) { return i; }, all, 128, P.pack + L.w2, L.n2pad, P.pack + L.b2,
+                    L.n2, os, tid);
+      for (int k = 0; k < u; ++k) {
+        const int pk = phys(d + k);
+        float y1 = ys[pk * FT + tid];
+        if (L.scaled) {
+          float sc = softplus_acc(os[(u + k) * FT + tid]);
+          sc = fminf(fmaxf(sc, 1e-3f), 1e3f);
+          y1 = y1 * sc;
+        }
+        ys[pk * FT + tid] = y1 + os[k * FT + tid];
+      }
+    }
+    if (live)
+      for (int i = 0; i < D; ++i) {
+        float v = ys[i * FT + tid];
+        if (P.pre) v = fmaf(v, P.pre[D + i], P.pre[i]);  // samples * pre_amp + pre_offset (model.py:272-273)
+        out[r * ldo + i] = v;
+      }
+  }
+}
+
+template <typename ET>
+__global__ void __launch_bounds__(FT)
+rqspline_sample_kernel(RQParams P, const ET* __restrict__ eps, long long ld, float* __restrict__ out,
+                       long long ldo, long long nrows) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int D = P.D, K = P.K;
+  float* ys = smem;
+  float* bufA = ys + (size_t)D * FT;
+  float* bufB = bufA + (size_t)P.maxw * FT;
+  float* ps = bufB + (size_t)P.maxw * FT;
+  auto ident = [](int i) { return i; };
+  auto all = [](int) { return true; };
+  const float sT = sqrtf(P.T);  // MultivariateNormalFullCovariance(cov = T I): scale sqrt(T) (flows.py:264-269)
+  for (long long t0 = (long long)blockIdx.x * FT; t0 < nrows; t0 += (long long)gridDim.x * FT) {
+    const long long r = t0 + tid;
+    const bool live = r < nrows;
+    const long long rr = live ? r : t0;
+    for (int i = 0; i < D; ++i) ys[i * FT + tid] = sT * (float)eps[rr * ld + i];
+    for (int i = 0; i < P.nlayers; ++i) {
+      const RQLayer L = P.layers[i];
+      const int par = i & 1;
+      auto visible = [&](int j) { return ((j & 1) == 1) != (par == 1); };
+      // scalar affine inverse, all dims
+      for (int j = 0; j < D; ++j) {
+        const float sc = __ldg(P.pack + L.scales + j), sh = __ldg(P.pack + L.shifts + j);
+        ys[j * FT + tid] = (ys[j * FT + tid] - sh) / sc;
+      }
+      // conditioner on the pass-through features (unchanged by this layer in either direction)
+      const float* cur = ys;
+      float* nxt = bufA;
+      for (int m = 0; m < P.nact; ++m) {
+        if (m == 0)
+          dense_cols<1>(cur, ident, visible, P.width[0], P.pack + L.w[0], P.wpad[1], P.pack + L.b[0],
+                        P.width[1], nxt, tid);
+        else
+          dense_cols<1>(cur, ident, all, P.width[m], P.pack + L.w[m], P.wpad[m + 1], P.pack + L.b[m],
+                        P.width[m + 1], nxt, tid);
+        cur = nxt;
+        nxt = (nxt == bufA) ? bufB : bufA;
+      }
+      int blk = 0;
+      const size_t blk_floats = (size_t)P.in_last * P.npar_pad + P.npar_pad;
+      for (int j = 0; j < D; ++j) {
+        if (visible(j)) continue;
+        const float* Mj = P.pack + L.fused + blk * blk_floats;
+        const float* cj = Mj + (size_t)P.in_last * P.npar_pad;
+        if (P.nact == 0)
+          dense_cols<0>(ys, ident, visible, P.in_last, Mj, P.npar_pad, cj, P.npar, ps, tid);
+        else
+          dense_cols<0>(cur, ident, all, P.in_last, Mj, P.npar_pad, cj, P.npar, ps, tid);
+        ys[j * FT + tid] = rqs_inverse(ys[j * FT + tid], ps, tid, K, P.lo, P.hi);
+        ++blk;
+      }
+    }
+    if (live)
+      for (int i = 0; i < D; ++i) {
+        float v = ys[i * FT + tid];
+        if (P.pre) v = fmaf(v, P.pre[D + i], P.pre[i]);
+        out[r * ldo + i] = v;
+      }
+  }
+}
+
+static int sample_grid(int device, long long n, size_t smem) {
+  long long nfl, rpc;
+  plan_grid(device, n, smem, &nfl, &rpc);
+  const long long tiles = (n + FT - 1) / FT;
+  return (int)(nfl < tiles ? nfl : tiles);
+}
+
+int flow_sample_run(Flow* f, float T, const void* eps, int eps_dtype, long long ld, long long n, float* out,
+                    long long ldo, cudaStream_t st) {
+  if (n <= 0) return HB_OK;
+  const hb_flow_desc& ds = f->desc;
+  if (ds.kind == HB_FLOW_REALNVP) {
+    RealNVPSimtParams P;
+    int rc = realnvp_simt_prepare(f, &P);
+    if (rc) return rc;
+    P.T = T;
+    const size_t smem = ((size_t)P.D + 128 + 2 * (size_t)P.u) * FT * sizeof(float);
+    if (smem > 227 * 1024) {
+      set_error("RealNVP sample: ndim too large for shared memory");
+      return HB_ERR_UNSUPPORTED;
+    }
+    const int grid = sample_grid(f->device, n, smem);
+    cudaFuncSetAttribute(realnvp_sample_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(realnvp_sample_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    timing_begin(st);
+    if (eps_dtype == HB_F32)
+      realnvp_sample_kernel<float><<<grid, FT, smem, st>>>(P, (const float*)eps, ld, out, ldo, n);
+    else
+      realnvp_sample_kernel<double><<<grid, FT, smem, st>>>(P, (const double*)eps, ld, out, ldo, n);
+    timing_end(st);
+  } else {
+    RQParams P;
+    rq_params(f, T, &P);
+    const size_t smem = ((size_t)P.D + 2 * (size_t)P.maxw + P.npar_pad) * FT * sizeof(float);
+    if (smem > 227 * 1024) {
+      set_error("RQSpline sample: ndim / hidden sizes too large for shared memory");
+      return HB_ERR_UNSUPPORTED;
+    }
+    const int grid = sample_grid(f->device, n, smem);
+    cudaFuncSetAttribute(rqspline_sample_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(rqspline_sample_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    timing_begin(st);
+    if (eps_dtype == HB_F32)
+      rqspline_sample_kernel<float><<<grid, FT, smem, st>>>(P, (const float*)eps, ld, out, ldo, n);
+    else
+      rqspline_sample_kernel<double><<<grid, FT, smem, st>>>(P, (const double*)eps, ld, out, ldo, n);
+    timing_end(st);
+  }
+  count_launch();
+  HB_CUDA(cudaGetLastError());
   return HB_OK;
 }
 

@@ -115,6 +115,9 @@ int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, l
                    const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
                    const int64_t* start, long long chain_lo, long long chain_hi, long long a,
                    long long b, cudaStream_t st);
+// sampling direction: out[r][0..ndim) = flow(eps[r]) for standard-normal draws eps (f32 / f64), generic SIMT kernels
+int flow_sample_run(Flow* f, float T, const void* eps, int eps_dtype, long long ld, long long n, float* out,
+                    long long ldo, cudaStream_t st);
 int realnvp_tc_prepare(Flow* f);  // builds tc_image; sets tc_ok
 int rqspline_prepare(Flow* f);
 void realnvp_tc_release(Flow* f);

@@ -221,9 +221,51 @@ class FlowModel(Model):
                                        ref.shape[0], ref.ld, out.ctypes.data, _lib.HB_MEM_HOST, None))
         return out[0] if one_d else out
 
-    def sample(self, n_sample, rng_key=None):
-        raise NotImplementedError(
-            "FlowModel.sample (harmonic/model.py:239-275) is outside the accelerated path")
+    # ------------------------------------------------------------------ harmonic/model.py:239-275
+    def sample(self, n_sample, rng_key=None, eps=None):
+        """Samples from the trained flow at ``self.temperature`` -> (n_sample, ndim) float32.
+
+        The reference draws the base Gaussian with a JAX PRNG key; here the standard-normal draws come from
+        torch's Philox generator on the GPU, seeded from ``rng_key`` (an int, or any array whose integer
+        contents are folded into a seed; default 0), so streams differ from JAX's but the transform is the
+        same.  ``eps`` (n_sample, ndim) supplies the standard-normal draws explicitly (numpy -> numpy out,
+        CUDA tensor -> torch CUDA tensor out): the call is then deterministic."""
+        self._check_temperature()
+        if not self.fitted:
+            raise ValueError("Model not fitted.")
+        lib = _lib.require_gpu()
+        n_sample = int(n_sample)
+        if n_sample < 0:
+            raise ValueError("n_sample must be non-negative.")
+        if eps is not None and not hasattr(eps, "__cuda_array_interface__"):
+            ea = np.asarray(eps)
+            if ea.ndim != 2 or ea.shape[1] != self.ndim or ea.shape[0] != n_sample:
+                raise ValueError("eps must have shape (n_sample, ndim).")
+            ref = _lib.ArrayRef(ea, want_2d=True)
+            out = np.empty((n_sample, self.ndim), dtype=np.float32)
+            _lib.check(lib.hb_flow_sample(self._get_handle(), self.temperature, ref.ptr, ref.dtype, n_sample, ref.ld,
+                                          out.ctypes.data, _lib.HB_MEM_HOST, None))
+            return out
+        import torch
+        if eps is None:
+            dev = self.device
+            seed = 0 if rng_key is None else int(np.sum(np.asarray(rng_key, dtype=np.uint64).ravel()
+                                                        * np.uint64(0x9E3779B97F4A7C15)) % np.uint64(2**63))
+            g = torch.Generator(device="cuda:%d" % dev)
+            g.manual_seed(seed)
+            e = torch.randn((n_sample, self.ndim), generator=g, device="cuda:%d" % dev, dtype=torch.float32)
+            to_host = True
+        else:
+            e, to_host = eps, False
+            if tuple(e.shape) != (n_sample, self.ndim):
+                raise ValueError("eps must have shape (n_sample, ndim).")
+        ref = _lib.ArrayRef(e, want_2d=True)
+        dev = ref.device if ref.device is not None else self.device
+        out = torch.empty((n_sample, self.ndim), dtype=torch.float32, device="cuda:%d" % dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.hb_flow_sample(self._get_handle(dev), self.temperature, ref.ptr, ref.dtype, n_sample, ref.ld,
+                                      out.data_ptr(), _lib.HB_MEM_DEVICE, stream))
+        return out.cpu().numpy() if to_host else out
 
 
 def _to_numpy_tree(tree):

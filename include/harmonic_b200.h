@@ -121,6 +121,14 @@ int hb_flow_uses_tcgen05(const hb_flow* flow);
 int hb_flow_predict(hb_flow* flow, float temperature, const void* x, int x_dtype, int x_mem,
                     int64_t n, int64_t ld, float* out, int out_mem, void* stream);
 
+/* Replaces FlowModel.sample (harmonic/model.py:239-275; flows.py:118-138, 290-313): out[i][0..ndim) = the flow
+ * in the sampling direction applied to the base draw built from the standard-normal row eps[i] (RealNVP:
+ * T * eps, RQSpline: sqrt(T) * eps), de-standardised (x * pre_amp + pre_offset) when the flow standardises.
+ * The random draws are the caller's (the reference takes a JAX PRNG key), so the call is deterministic.
+ * eps: (n, ld_eps >= ndim) HB_F32 / HB_F64; out: (n, ndim) float32, contiguous; both in `mem`. */
+int hb_flow_sample(hb_flow* flow, float temperature, const void* eps, int eps_dtype, int64_t n,
+                   int64_t ld_eps, float* out, int mem, void* stream);
+
 /* Streaming per-chain state of Evidence (harmonic/evidence.py:65-67,83-85): for every chain the
  * max-rescaled pair (m, s) with ln sum_i exp(lnarg_i) = m + ln s, the sample count n and the NaN
  * count; plus the per-call scalars. */

@@ -26,6 +26,8 @@ for name, m, path in cases:
     util.assert_evidence_close(ev, ref)
     p = m.predict(ch.samples[:777])
     util.check_predict(m, ch.samples[:777], p)
+    eps = np.random.default_rng(2).standard_normal((301, m.ndim))
+    util.check_sample(m, eps, m.sample(301, eps=eps))
     print("ok", name, ev.ln_evidence_inv)
 ev = hm.Evidence(5, cases[0][1])
 ev.add_lnpred(np.random.default_rng(0).standard_normal(5000), np.random.default_rng(1).standard_normal(5000),

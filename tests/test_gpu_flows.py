@@ -205,3 +205,73 @@ def test_realnvp_tcgen05_fused_vs_oracle_and_auto_path():
     ev.add_chains(ch)
     ref = util.oracle_evidence(m, ch)
     util.assert_evidence_close(ev, ref)
+
+
+# ------------------------------------------------------------------ FlowModel.sample (harmonic/model.py:239-275)
+@pytest.mark.parametrize("ndim", [2, 5, 17, 64])
+@pytest.mark.parametrize("standardize", [False, True])
+def test_realnvp_sample_vs_oracle(ndim, standardize):
+    m = util.make_realnvp(ndim, seed=12, standardize=standardize, ws=0.4, temperature=0.8)
+    eps = samples(3000, ndim, seed=13)
+    got = m.sample(3000, eps=eps)
+    assert got.dtype == np.float32 and got.shape == (3000, ndim)
+    util.check_sample(m, eps, got)
+    # float32 draws give the same samples as float64 draws rounded to float32
+    got32 = m.sample(3000, eps=eps.astype(np.float32))
+    util.check_sample(m, eps.astype(np.float32), got32)
+
+
+@pytest.mark.parametrize("ndim,hidden,layers", [(2, (64, 64), 8), (3, (16, 16), 3), (5, (32,), 2), (6, (8, 8, 8), 2), (4, (), 3)])
+@pytest.mark.parametrize("standardize", [False, True])
+def test_rqspline_sample_vs_oracle(ndim, hidden, layers, standardize):
+    m = util.make_rqspline(ndim, layers, 8, hidden, seed=14, standardize=standardize, ws=0.4, temperature=0.9)
+    eps = samples(2000, ndim, seed=15, scale=1.5)
+    eps[0, :] = 40.0   # linear tails of the spline
+    eps[1, :] = -40.0
+    got = m.sample(2000, eps=eps)
+    util.check_sample(m, eps, got)
+
+
+@pytest.mark.parametrize("kind", ["realnvp", "rqspline"])
+def test_sample_round_trip_and_device_path(kind):
+    """predict(sample(eps)) against the change-of-variables value is covered by the oracle tests; here: the device
+    path (CUDA tensor in -> CUDA tensor out) equals the host path, NaN draws give NaN rows, and ln phi of the
+    samples equals the oracle's ln phi at the same points (the two directions share one weight pack)."""
+    import torch
+    ndim = 5
+    m = (util.make_realnvp(ndim, seed=21, standardize=True, ws=0.4) if kind == "realnvp"
+         else util.make_rqspline(ndim, 3, 8, (16, 16), seed=21, standardize=True, ws=0.4))
+    eps = samples(4096 + 37, ndim, seed=22).astype(np.float32)
+    eps[5, 2] = np.nan
+    host = m.sample(eps.shape[0], eps=eps)
+    dev = m.sample(eps.shape[0], eps=torch.from_numpy(eps).cuda())
+    assert dev.is_cuda
+    np.testing.assert_array_equal(np.isnan(host), np.isnan(dev.cpu().numpy()))
+    ok = ~np.isnan(host)
+    np.testing.assert_array_equal(host[ok], dev.cpu().numpy()[ok])
+    assert np.isnan(host[5]).any()
+    good = np.delete(host, 5, axis=0)
+    util.check_predict(m, good, m.predict(good))
+
+
+def test_sample_rng_moments_and_guards():
+    """tests/test_flow_model.py:209-251: samples of a flow trained on a Gaussian reproduce its moments; a lower
+    temperature concentrates them.  Uses the committed cfg1 fixture (trained on N(0, Sigma), ndim 5)."""
+    from bench_workloads import init_cov, load_cfg1_model
+    m = load_cfg1_model(1.0)
+    x = m.sample(200000, rng_key=10)
+    assert x.shape == (200000, 5) and x.dtype == np.float32
+    cov = init_cov(5)
+    assert np.all(np.abs(x.mean(axis=0)) < 0.15)
+    assert np.all(np.abs(x.var(axis=0) - np.diag(cov)) < 0.15)
+    m.temperature = 0.8
+    xc = m.sample(200000, rng_key=10)
+    assert np.all(xc.var(axis=0) < x.var(axis=0))
+    np.testing.assert_array_equal(m.sample(100, rng_key=3), m.sample(100, rng_key=3))
+    assert not np.array_equal(m.sample(100, rng_key=3), m.sample(100, rng_key=4))
+    m.temperature = 1.5
+    with pytest.raises(ValueError):
+        m.sample(10)
+    m.temperature = 0.8
+    with pytest.raises(ValueError):
+        m.sample(10, eps=np.zeros((10, 4)))

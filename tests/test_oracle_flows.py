@@ -66,3 +66,58 @@ def test_predict_temperature_guards():
     spec["temperature"] = 0.0
     with pytest.raises(ValueError):
         of.predict(spec, np.zeros((1, 2)))
+
+
+# ------------------------------------------------------------------ sampling direction (model.py:239-275)
+def _fd_logdet(spec, e0):
+    D = e0.size
+    J = np.zeros((D, D))
+    h = 1e-6
+    for i in range(D):
+        de = np.zeros(D)
+        de[i] = h
+        J[:, i] = (of.sample_transform(spec, (e0 + de)[None, :])[0] - of.sample_transform(spec, (e0 - de)[None, :])[0]) / (2 * h)
+    return np.linalg.slogdet(J)[1]
+
+
+@pytest.mark.parametrize("kind,ndim", [("realnvp", 2), ("realnvp", 5), ("realnvp", 16), ("rqspline", 2), ("rqspline", 5)])
+def test_sample_direction_is_the_inverse_of_log_prob(kind, ndim):
+    """Change of variables: log_prob(sample(eps)) = ln N(eps; 0, I) - ln |det d sample / d eps| with the Jacobian
+    taken by finite differences, i.e. the sampling direction inverts the log_prob direction including every
+    log-det term, temperature and (de)standardisation."""
+    rng = np.random.default_rng(7)
+    common = dict(standardize=True, pre_offset=rng.standard_normal(ndim) * 0.3, pre_amp=0.5 + rng.random(ndim))
+    if kind == "realnvp":
+        spec = dict(kind=kind, params=export.random_realnvp_params(ndim, 2, 4, seed=1, weight_scale=0.5),
+                    temperature=0.8, n_scaled_layers=2, n_unscaled_layers=4, **common)
+    else:
+        spec = dict(kind=kind, params=export.random_rqspline_params(ndim, 3, 8, (16, 16), seed=2, weight_scale=0.6),
+                    temperature=0.7, n_layers=3, n_bins=8, hidden_size=[16, 16], spline_range=(-10.0, 10.0), **common)
+    eps = rng.standard_normal((4, ndim)) * 1.5
+    x = of.sample_transform(spec, eps)
+    lp = of.predict(spec, x)
+    for r in range(eps.shape[0]):
+        want = -0.5 * np.sum(eps[r] ** 2) - 0.5 * ndim * np.log(2 * np.pi) - _fd_logdet(spec, eps[r])
+        assert lp[r] == pytest.approx(want, abs=2e-6 * max(1.0, abs(want)))
+
+
+def test_rqspline_inverse_covers_tails_and_nan():
+    """Linear tails outside the spline range and NaN propagation of the inverse spline."""
+    rng = np.random.default_rng(3)
+    K = 8
+    P = rng.standard_normal((6, 3 * K + 1))
+    x = np.array([-25.0, -10.0, -3.0, 4.0, 10.0, 31.0])
+    y, _ = of._rqs_forward(x, P, K, -10.0, 10.0, np.float64)
+    back = of._rqs_inverse(y, P, K, -10.0, 10.0, np.float64)
+    np.testing.assert_allclose(back, x, rtol=1e-10, atol=1e-10)
+    assert np.isnan(of._rqs_inverse(np.array([np.nan]), P[:1], K, -10.0, 10.0, np.float64))[0]
+
+
+def test_sample_temperature_guards():
+    spec = dict(kind="realnvp", params=export.random_realnvp_params(2, 1, 1, seed=1), temperature=1.2,
+                n_scaled_layers=1, n_unscaled_layers=1)
+    with pytest.raises(ValueError):
+        of.sample_transform(spec, np.zeros((1, 2)))
+    spec["temperature"] = 0.0
+    with pytest.raises(ValueError):
+        of.sample_transform(spec, np.zeros((1, 2)))

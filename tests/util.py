@@ -31,6 +31,28 @@ def gaussian_chains(ndim, nchains, nsamples, seed=0, ragged=False):
     return ch
 
 
+def oracle_sample(model, eps, dtype=np.float64):
+    return of.sample_transform(model.oracle_spec(), eps, dtype)
+
+
+def check_sample(model, eps, got, rel=1e-5):
+    """got (n, ndim) vs the float64 oracle of FlowModel.sample for the same standard-normal draws: 1e-5
+    relative per coordinate (floor |x| at 1), widened by 3x the deviation of the float32 restatement."""
+    want = oracle_sample(model, eps, np.float64)
+    w32 = oracle_sample(model, eps, np.float32).astype(np.float64)
+    got = np.asarray(got, dtype=np.float64)
+    assert got.shape == want.shape
+    nan_w = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan_w), "NaN pattern differs"
+    ok = ~nan_w
+    den = np.maximum(np.abs(want[ok]), 1.0)
+    err = np.abs(got[ok] - want[ok]) / den
+    tol = rel + 3.0 * np.abs(w32[ok] - want[ok]) / den
+    bad = err > tol
+    assert not bad.any(), "max rel err %.3g, %d coordinates over tolerance" % (err.max(), int(bad.sum()))
+    return 0.0 if err.size == 0 else float(err.max())
+
+
 def check_predict(model, x, got, rel=1e-5, slack_mult=1.0):
     """got vs the float64 oracle at the north_star tolerance (1e-5 relative), widened per sample
     where float32 evaluation is ill-conditioned: by 3x the deviation of the float32 restatement (the
