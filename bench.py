@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- samples/sec folded into ln Z (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py --gpus N --steps K --warmup W [--workload cfg4|cfg2|cfg3|cfg5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload cfg4|cfg2|cfg2x|cfg3|cfg5] [--impl reference]
 
 A "step" is one pass of the hot path over one batch of synthetic chains: evaluate the flow on
 every sample, fold ln phi - ln posterior into the per-chain state, (N > 1: one all-gather of the
@@ -138,7 +138,7 @@ def cpu_reference_pass(name, model, nchains, per_chain, seed, threads):
 
 def cpu_sample_shape(name):
     # about 10-30 s of CPU work on a 16-core host
-    return {"cfg4": (160, 25000), "cfg3": (400, 20000), "cfg1": (100, 5000), "cfg2": (20, 10000),
+    return {"cfg4": (160, 25000), "cfg3": (400, 20000), "cfg1": (100, 5000), "cfg2": (20, 10000), "cfg2x": (40, 25000),
             "cfg5": (1000, 20000)}[name]
 
 
@@ -182,13 +182,14 @@ def workload_config(name, n_gpus, nchains, per_chain):
         "cfg3": "cfg3: RealNVP 6+2, ndim 5, T=0.9",
         "cfg1": "cfg1: RealNVP 2+4, ndim 5, T=0.8",
         "cfg2": "cfg2: RQSpline 8 layers x 8 bins, hidden [64,64], ndim 2 (Rosenbrock), T=0.9",
+        "cfg2x": "cfg2 with the example's architecture: RQSpline 3 layers x 8 bins, hidden [32,32], ndim 2, T=0.9",
         "cfg5": "cfg5: accumulation only, precomputed ln phi and ln posterior (float32)",
     }[name]
     return {"workload": desc, "nchains_per_gpu": nchains, "samples_per_chain": per_chain,
             "samples_per_gpu": nchains * per_chain, "sharding": "chains sharded across %d GPU(s), one "
             "all-gather of per-chain partials" % n_gpus,
             "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (
-                nchains * per_chain * {"cfg4": 260, "cfg3": 24, "cfg1": 24, "cfg2": 12, "cfg5": 8}[name] / 1e9)}
+                nchains * per_chain * {"cfg4": 260, "cfg3": 24, "cfg1": 24, "cfg2": 12, "cfg2x": 12, "cfg5": 8}[name] / 1e9)}
 
 
 # ------------------------------------------------------------------------------------- GPU arm
@@ -197,7 +198,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg3", "cfg2", "cfg5", "cfg1"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg3", "cfg2", "cfg2x", "cfg5", "cfg1"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale samples per chain (debug)")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05"])
@@ -371,10 +372,20 @@ def main():
         peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
         roof = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None, "traffic": None,
-                "kernel": {"cfg2": "rqspline_fast_kernel", "cfg3": "realnvp_small_kernel",
+                "kernel": {"cfg2": "rqspline_fast_kernel", "cfg2x": "rqspline_fast_kernel", "cfg3": "realnvp_small_kernel",
                            "cfg1": "realnvp_small_kernel"}.get(name, "simt flow kernel"), "kernel_ms": kms,
                 "peak_source": "FP32 CUDA-core FMA peak at the max SM clock (nominal)",
                 "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
+        if name in ("cfg2", "cfg2x") and ach:
+            # SURVEY.md 8(d) counts the reference's dense conditioner (all D rows of the (D, 3K+1) output, two
+            # separate last Denses).  The kernel pre-multiplies the last MLP Dense with the output Dense (no
+            # activation between them, harmonic/flows.py:357,434-438) and evaluates only the transformed rows,
+            # so it EXECUTES fewer FLOPs than the algorithmic count: frac can exceed 1; frac_executed is the
+            # fraction of the FP32 peak actually sustained (the spline's MUFU work is not counted in either).
+            L, h = (8, 64) if name == "cfg2" else (3, 32)
+            ex = L * 2.0 * (2 * 2 + 2 * h + h * 25)
+            roof["executed_flop_per_sample"] = ex
+            roof["frac_executed"] = roof["frac"] * ex / wl.FLOP_PER_SAMPLE[name]
 
     cpu = None
     if not args.no_cpu and world == 1:

@@ -53,8 +53,8 @@ def load_cfg1_model(temperature=0.8):
     m.load_params(params, z["pre_offset"], z["pre_amp"])
     return m
 
-FLOP_PER_SAMPLE = {"cfg4": 114688.0, "cfg3": 14848.0, "cfg1": 9216.0, "cfg2": 118848.0}
-BYTES_PER_SAMPLE = {"cfg4": 260.0, "cfg3": 24.0, "cfg1": 24.0, "cfg2": 12.0, "cfg5": 8.0}
+FLOP_PER_SAMPLE = {"cfg4": 114688.0, "cfg3": 14848.0, "cfg1": 9216.0, "cfg2": 118848.0, "cfg2x": 16152.0}
+BYTES_PER_SAMPLE = {"cfg4": 260.0, "cfg3": 24.0, "cfg1": 24.0, "cfg2": 12.0, "cfg2x": 12.0, "cfg5": 8.0}
 
 
 def init_cov(ndim, seed=10):
@@ -76,12 +76,14 @@ def make_model(name):
         return load_cfg1_model(0.8)
     if name == "cfg2":
         return make_rqspline(2, 8, 8, (64, 64), seed=2, standardize=False, temperature=0.9, ws=0.15)
+    if name == "cfg2x":  # the example's architecture (examples/rosenbrock.py:175-178): 3 layers, hidden [32, 32]
+        return make_rqspline(2, 3, 8, (32, 32), seed=2, standardize=False, temperature=0.9, ws=0.15)
     raise ValueError(name)
 
 
 def default_shape(name):
     """(nchains, samples per chain) per GPU."""
-    return {"cfg4": (1000, 100000), "cfg3": (1000, 10000), "cfg1": (100, 5000), "cfg2": (1000, 100000),
+    return {"cfg4": (1000, 100000), "cfg3": (1000, 10000), "cfg1": (100, 5000), "cfg2": (1000, 100000), "cfg2x": (1000, 100000),
             "cfg5": (10000, 100000)}[name]
 
 
@@ -105,7 +107,7 @@ def rosenbrock_host(n, seed):
 
 
 def host_sample(name, n, seed=0):
-    if name == "cfg2":
+    if name in ("cfg2", "cfg2x"):
         return rosenbrock_host(n, seed)
     ndim = {"cfg4": 64, "cfg3": 5, "cfg1": 5}[name]
     return gaussian_host(ndim, n, seed)
@@ -129,7 +131,7 @@ def device_data(name, nchains, per_chain, device, seed=0):
             bad = torch.rand(b - a, generator=g, device=device) < 1e-4  # non-finite path
             lnphi[a:b][bad] = float("nan")
         return lnphi, lnp
-    if name == "cfg2":
+    if name in ("cfg2", "cfg2x"):
         x = torch.empty((n, 2), dtype=torch.float32, device=device)
         lnp = torch.empty(n, dtype=torch.float32, device=device)
         blk = 1 << 24
