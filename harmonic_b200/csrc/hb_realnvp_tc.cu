@@ -417,8 +417,13 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   const int nl = P.nlayers;
 #ifdef HB_TC_TRACE
   int tr_n = 0;
+#ifdef HB_TC_TRACE_SKEW  // the four warps of warpgroup 0 instead (warp skew at the barriers)
+  const bool tr_on = blockIdx.x == 0 && lane == 0 && warp < 4;
+  const int tr_s = warp;
+#else
   const bool tr_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp >= 9);
   const int tr_s = warp == 0 ? 0 : warp == 4 ? 1 : warp == 9 ? 2 : 3;
+#endif
 #endif
 
   // ---- one-time setup -------------------------------------------------------------------

@@ -1,7 +1,9 @@
 """Phase timeline of realnvp_tc_kernel on one SM (development aid).
 
 Build with  HB_NVCC_EXTRA=-DHB_TC_TRACE python harmonic_b200/build.py --force , run this on a B200, then
-rebuild without the flag.  CTA 0 records clock64() stamps from lane 0 of: epilogue warpgroup 0 / 1 (streams 0 / 1)
+rebuild without the flag.  With  HB_NVCC_EXTRA="-DHB_TC_TRACE -DHB_TC_TRACE_SKEW"  and  --skew  the four streams
+are the four warps of epilogue warpgroup 0 and the output is their spread at every stamp (round 1: ~80-120
+cycles at the barrier arrivals; the warp that shares its scheduler with no MMA / producer warp leads).  CTA 0 records clock64() stamps from lane 0 of: epilogue warpgroup 0 / 1 (streams 0 / 1)
 and the two MMA warps (streams 2 / 3).  Prints mean cycles per phase over steady-state tiles.
 """
 import ctypes as C
@@ -35,6 +37,21 @@ def main():
     fn = lib.hb_debug_trace_read
     fn.restype = C.c_int
     assert fn(buf.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p)) == 0
+    if "--skew" in sys.argv:
+        clk = [(buf[s, :n[s]] >> np.uint64(8)).astype(np.int64) for s in range(4)]
+        code = [(buf[s, :n[s]] & np.uint64(255)).astype(np.int64) for s in range(4)]
+        L = int(min(n))
+        assert all(np.array_equal(code[0][:L], code[s][:L]) for s in range(4)), "streams differ"
+        c = np.stack([clk[s][:L] for s in range(4)])
+        for cd in sorted(set(code[0][:L])):
+            idx = np.nonzero(code[0][:L] == cd)[0]
+            idx = idx[idx >= L // 4]
+            if len(idx):
+                sp = c[:, idx].max(axis=0) - c[:, idx].min(axis=0)
+                rel = c[:, idx] - c[:, idx].min(axis=0, keepdims=True)
+                print("%-28s n=%4d  spread mean %6.0f max %6d | mean lateness per warp %s" % (
+                    NAMES.get(cd, cd), len(idx), sp.mean(), sp.max(), np.round(rel.mean(axis=1)).astype(int)))
+        return
     for s in range(4):
         ev = buf[s, :n[s]]
         clk = (ev >> np.uint64(8)).astype(np.int64)
