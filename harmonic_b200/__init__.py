@@ -5,6 +5,7 @@ from . import logs
 from . import chains
 from . import model
 from . import evidence
+from . import utils
 from .chains import Chains
 from .evidence import Evidence, Shifting
 

@@ -182,3 +182,39 @@ def test_evidence_pickle_drops_handles(tmp_path):
     ev2 = hm.Evidence.deserialize(fn)
     assert ev2._acc is None and ev2.shift == hm.Shifting.MAX_SHIFT
     np.testing.assert_array_equal(ev2._partials, ev._partials)
+
+
+def test_split_data_views_and_guards():
+    """harmonic/utils.py:129-200 and tests/test_utils.py:8-120: first chains train, rest test; argument checks;
+    here both halves are views of the parent's arrays."""
+    import harmonic_b200 as hm
+    ndim, nsamples, nchains = 5, 100, 200
+    rng = np.random.default_rng(3)
+    samples = rng.standard_normal((nchains, nsamples, ndim))
+    lnp = -0.5 * np.sum(samples * samples, axis=2)
+    ch = hm.Chains(ndim)
+    ch.add_chains_3d(samples, lnp)
+    for prop in (0.5, 0.75):
+        tr, te = hm.utils.split_data(ch, training_proportion=prop)
+        ntr = int(nchains * prop)
+        assert tr.nchains == ntr and te.nchains == nchains - ntr
+        assert tr.nsamples == nsamples * ntr and te.nsamples == nsamples * (nchains - ntr)
+        assert tr.start_indices == [i * nsamples for i in range(ntr + 1)]
+        assert te.start_indices == [i * nsamples for i in range(nchains - ntr + 1)]
+        assert tr.samples.shape == (nsamples * ntr, ndim) and te.ln_posterior.shape == (nsamples * (nchains - ntr),)
+        i = int(rng.integers(nsamples * ntr))
+        assert tr.samples[i, 3] == samples[i // nsamples, i % nsamples, 3]
+        j = int(rng.integers(nsamples * (nchains - ntr)))
+        assert te.samples[j, 3] == samples[j // nsamples + ntr, j % nsamples, 3]
+        assert te.ln_posterior[j] == lnp[j // nsamples + ntr, j % nsamples]
+        assert np.shares_memory(tr.samples, ch.samples) and np.shares_memory(te.samples, ch.samples)
+    for bad in (-0.1, 0.0, 1.0, 1.5, 1e-10):
+        with pytest.raises(ValueError):
+            hm.utils.split_data(ch, training_proportion=bad)
+    # ragged chains keep their own lengths
+    rg = hm.Chains(2)
+    for n in (3, 7, 5, 2):
+        rg.add_chain(rng.standard_normal((n, 2)), rng.standard_normal(n))
+    a, b = hm.utils.split_data(rg, 0.5)
+    assert a.start_indices == [0, 3, 10] and b.start_indices == [0, 5, 7]
+    np.testing.assert_array_equal(b.samples, rg.samples[10:])
