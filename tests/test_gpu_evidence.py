@@ -194,3 +194,25 @@ def test_errors():
     ch = util.gaussian_chains(2, 5, 10)
     with pytest.raises(ValueError):
         ev.add_chains(ch)  # nchains mismatch
+
+
+def test_split_data_device_resident_chains():
+    """utils.split_data on device-resident chains is index arithmetic; the evidence of the test half equals the
+    host-chains result."""
+    import torch
+    from tests import util as u
+    ndim = 5
+    m = u.make_realnvp(ndim, seed=2, standardize=True, ws=0.3)
+    ch = u.gaussian_chains(ndim, 20, 400, seed=5, ragged=True)
+    _, te = hm.utils.split_data(ch, 0.5)
+    ev_h = hm.Evidence(te.nchains, m)
+    ev_h.add_chains(te)
+    xs = torch.from_numpy(ch.samples.astype(np.float32)).cuda()
+    ys = torch.from_numpy(ch.ln_posterior.astype(np.float32)).cuda()
+    dch = hm.Chains.from_arrays(xs, ys, ch.start_indices)
+    _, dte = hm.utils.split_data(dch, 0.5)
+    assert dte.samples.is_cuda and dte.samples.data_ptr() == xs[ch.start_indices[10]:].data_ptr()
+    ev_d = hm.Evidence(dte.nchains, m)
+    ev_d.add_chains(dte)
+    assert ev_d.ln_evidence_inv == pytest.approx(ev_h.ln_evidence_inv, abs=1e-5)
+    np.testing.assert_allclose(ev_d.nsamples_per_chain, ev_h.nsamples_per_chain)
