@@ -275,3 +275,49 @@ def test_sample_rng_moments_and_guards():
     m.temperature = 0.8
     with pytest.raises(ValueError):
         m.sample(10, eps=np.zeros((10, 4)))
+
+
+# ------------------------------------------------------------------ tcgen05 path: shapes at the edges of support
+@pytest.mark.parametrize("layers", [(4, 4), (2, 6), (8, 0), (1, 7)])
+def test_realnvp_tcgen05_layer_limits(layers):
+    """Up to 8 coupling layers run on the tensor path (7 frozen columns + the bias column fill one K = 8 step),
+    all-scaled and mostly-unscaled stacks; 9 layers fall back to the CUDA-core kernels."""
+    m = util.make_realnvp(64, layers[0], layers[1], seed=31, standardize=True, ws=0.3, temperature=0.7)
+    lib = _lib.load()
+    assert lib.hb_flow_uses_tcgen05(m._get_handle()) == 1
+    x = samples(2500, 64, seed=32)
+    util.check_predict(m, x, m.predict(x))
+
+
+def test_realnvp_nine_layers_leave_the_tensor_path():
+    m = util.make_realnvp(64, 3, 6, seed=33, ws=0.3)
+    lib = _lib.load()
+    assert lib.hb_flow_uses_tcgen05(m._get_handle()) == 0
+    x = samples(700, 64, seed=34)
+    util.check_predict(m, x, m.predict(x))
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    with pytest.raises(NotImplementedError):
+        m.predict(x)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_realnvp_tcgen05_device_strided_and_f64(dtype):
+    """Device-resident samples with a row stride larger than ndim (ld = 80) and float64 storage: both are read in
+    place by the tensor-path kernel (per-row loads; float64 is demoted on load as JAX does)."""
+    import torch
+    m = util.make_realnvp(64, seed=35, standardize=True, ws=0.3)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    n = 3000
+    big = torch.from_numpy(samples(n, 80, seed=36)).to(getattr(torch, dtype)).cuda()
+    view = big[:, 8:72]
+    assert view.stride(0) == 80
+    got = m.predict(view).cpu().numpy()
+    util.check_predict(m, view.cpu().numpy().astype(np.float32 if dtype == "float32" else np.float64), got)
+    # the same rows through the fused path, ragged chains
+    lnp = torch.from_numpy(np.random.default_rng(1).standard_normal(n)).to(getattr(torch, dtype)).cuda()
+    start = [0, 5, 900, 1300, 2100, n]
+    ev = hm.Evidence(5, m)
+    ev.add_chains(hm.Chains.from_arrays(view, lnp, start))
+    host = hm.Chains.from_arrays(view.cpu().numpy(), lnp.cpu().numpy(), start)
+    ref = util.oracle_evidence(m, host)
+    util.assert_evidence_close(ev, ref)
