@@ -7,6 +7,7 @@ cycles at the barrier arrivals; the warp that shares its scheduler with no MMA /
 and the two MMA warps (streams 2 / 3).  Prints mean cycles per phase over steady-state tiles.
 """
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -28,7 +29,7 @@ def main():
     lib = _lib.load()
     m = wl.make_model("cfg4")
     m.kernel_path = _lib.HB_PATH_TCGEN05
-    x, _ = wl.device_data("cfg4", 148 * 2, 128 * 24, torch.device("cuda", 0), seed=1)
+    x, _ = wl.device_data("cfg4", 148 * 2, 128 * int(os.environ.get("HB_TRACE_TILES", "24")), torch.device("cuda", 0), seed=1)
     for _ in range(2):
         m.predict(x)
     torch.cuda.synchronize()
@@ -37,6 +38,9 @@ def main():
     fn = lib.hb_debug_trace_read
     fn.restype = C.c_int
     assert fn(buf.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p)) == 0
+    if "--raw" in sys.argv:  # dump (stream, clock, code) for offline analysis
+        np.save("gpurun_out/tc_trace_raw.npy", buf)
+        np.save("gpurun_out/tc_trace_n.npy", n)
     if "--skew" in sys.argv:
         clk = [(buf[s, :n[s]] >> np.uint64(8)).astype(np.int64) for s in range(4)]
         code = [(buf[s, :n[s]] & np.uint64(255)).astype(np.int64) for s in range(4)]
