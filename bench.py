@@ -171,7 +171,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -193,7 +193,28 @@ def workload_config(name, n_gpus, nchains, per_chain):
 
 
 # ------------------------------------------------------------------------------------- GPU arm
+_JSON_OUT = None
+
+
+def emit(text):
+    """The one JSON line goes to the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
+def claim_stdout():
+    """Libraries write banners to file descriptor 1 (NCCL prints its version there on communicator creation):
+    keep a private handle on the real stdout for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -405,7 +426,7 @@ def main():
         "result": {"ln_evidence_inv": float(ev.ln_evidence_inv), "ln_evidence_inv_var": float(ev.ln_evidence_inv_var),
                    "n_eff": float(ev.n_eff)},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
