@@ -376,7 +376,7 @@ def main():
         peak = float(peaks["bf16_tflops"]) / 2.0
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None,
-                # ncu --set full (profiles/r1_prof_tc_r1f_raw_summary.csv): 263 B of DRAM traffic per sample
+                # ncu --set full (profiles/r1_prof_tc_r1h_raw_summary.csv): 262.8 B of DRAM traffic per sample
                 # (algorithmic 260 B): the kernel is not memory bound
                 "traffic": 263.0 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
                 "kernel": "realnvp_tc_kernel", "kernel_ms": kms,
@@ -385,6 +385,8 @@ def main():
                 # terms, twice the TF32 rate); in TF32-rate time that is 2.21x the algorithmic count, so
                 # frac <= 0.45 for this scheme
                 "issued_mma_flop_factor": 3.32, "issued_tf32_time_factor": 2.21,
+                # ncu --set full of the same kernel (profiles/r1_prof_tc_r1h_raw_summary.csv)
+                "ncu_tensor_pipe_active_pct": 39.6, "ncu_issue_active_pct": 44.3,
                 "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
     else:
         # small-ndim flows run on the FP32 CUDA cores (tensor tiles would be >= 75 % padding):
