@@ -381,12 +381,12 @@ def main():
                 "traffic": 263.0 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
                 "kernel": "realnvp_tc_kernel", "kernel_ms": kms,
                 "peak_source": "TF32 dense = bf16 burst / 2, of %s" % peak_kind,
-                # issued: 1.11x as kind::tf32 (K 32 -> 40 in GEMM1) + 2.21x as kind::f16 (the two correction
-                # terms, twice the TF32 rate); in TF32-rate time that is 2.21x the algorithmic count, so
-                # frac <= 0.45 for this scheme
-                "issued_mma_flop_factor": 3.32, "issued_tf32_time_factor": 2.21,
-                # ncu --set full of the same kernel (profiles/r1_prof_tc_r1h_raw_summary.csv)
-                "ncu_tensor_pipe_active_pct": 39.6, "ncu_issue_active_pct": 44.3,
+                # issued: 0.54x as kind::tf32 (GEMM1 main term, K 32 -> 40) + 2.79x as kind::f16 (GEMM1 corrections,
+                # all of GEMM2); a tcgen05.mma costs max(~45, N/2) cycles whatever its kind (profiles/r1_mma_probe.txt):
+                # 10 x 64.4 + 24 x 45 = 1724 tensor-pipe cycles per 128-sample tile and layer => pipe bound 29.5 ms
+                # for 1e8 samples at 1.85 GHz, i.e. frac <= 0.47 for this instruction mix
+                "issued_mma_flop_factor": 3.32, "issued_tf32_time_factor": 1.93,
+                "mma_instructions_per_tile_layer": 34, "tensor_pipe_cycles_per_tile_layer": 1724,
                 "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
     else:
         # small-ndim flows run on the FP32 CUDA cores (tensor tiles would be >= 75 % padding):
@@ -422,7 +422,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32+f16 split (f32-equivalent products, f32 accumulate)" if (name == "cfg4" and args.path != "simt") else "f32",
+        "vs_baseline": None, "dtype": "tf32/f16 split (f32-equivalent products, f32 accumulate)" if (name == "cfg4" and args.path != "simt") else "f32",
         "data": "synthetic", "config": workload_config(name, world, nchains, per_chain),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "result": {"ln_evidence_inv": float(ev.ln_evidence_inv), "ln_evidence_inv_var": float(ev.ln_evidence_inv_var),

@@ -16,19 +16,19 @@
 //
 // Per coupling layer and tile
 //   GEMM1  H[128x128] = [x(0..31) | new(0..6) | 1] . W0'        A, B from shared memory, K = 40
-//   E1     h = leaky_relu(H), split hi/lo, back to TMEM          four 32-column quarters
-//   GEMM2  O[128xN2] += h[:, quarter] . [Wt|Ws][quarter, :]      A from TMEM, one K = 32 step per quarter
+//   E1     h = leaky_relu(H), compensated FP16 split, in place   eight 16-column chunks, TMEM loads prefetched
+//   GEMM2  O[128xN2] += h[:, quarter] . [Wt|Ws][quarter, :]      A from TMEM, 6 FP16 MMAs per K = 32 quarter
 //   E2     shift / softplus-clip scale epilogue on y1, log-det
-// Split-precision contraction with FP32 accumulation in TMEM: a.w ~= a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo),
-// hi = top 19 bits (a TF32 value), lo = exact remainder.  The main term a_hi.w_hi runs as kind::tf32;
-// the two correction terms only need ~11 significant bits per factor, so they run as ONE kind::f16
-// contraction over the concatenated K' = [a_lo | a_hi] . [w_hi ; w_lo] (an 11-bit TF32 significand is
-// exactly an FP16 significand).  The hi half of the FP16 operand is stored * 2^-11 and w_lo * 2^11, so
-// all four FP16 factors sit at the magnitude of a_lo / w_hi: normal halves for |a| in ~[0.1, 1.3e8];
-// below that the loss is an absolute 3e-8 |w| per product, above it satfinite conversion clamps and the
-// result degrades to plain TF32 accuracy instead of inf/NaN.  Same ~2^-22 product accuracy as a 3xTF32
-// split at 2/3 of the MMA count and operand traffic.  What remains against a float32 FMA chain is the
-// tensor cores' truncating accumulator (profiles/r1_tensor_accum_rounding.txt), see DESIGN.md 4.1.
+// Split-precision contractions with FP32 accumulation in TMEM, float32-equivalent products (~2^-22).
+// GEMM1: a.w ~= a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo), hi = top 19 bits (a TF32 value), lo = exact remainder; the
+// main term runs as kind::tf32 (any input magnitude), the two correction terms as ONE kind::f16 contraction over
+// K' = [a_lo | a_hi * 2^-11] . [w_hi ; w_lo * 2^11].
+// GEMM2: entirely kind::f16 (see the comment at H2_SCALE): hs = fp16(h * 2^-11), lo = h - 2^11 hs, and
+// h.w ~= hs.(w_hi 2^11) + hs.(w_lo 2^11) + lo.w_hi -- the SAME hs block feeds two MMAs.  A tcgen05.mma costs
+// max(~45, N/2) cycles whatever its kind (profiles/r1_mma_probe.txt), so for the N = 64 / 32 steps of GEMM2 the
+// instruction count is the resource: 6 FP16 MMAs (K = 16 each) per quarter instead of 4 TF32 + 4 FP16.
+// What remains against a float32 FMA chain is the tensor cores' truncating accumulator
+// (profiles/r1_tensor_accum_rounding.txt), see DESIGN.md 4.1.
 //
 // GEMM1 without re-staging activations.  The flow permutes by one position per layer
 // (harmonic/flows.py:65-66), so layer l conditions on ORIGINAL features l .. l+31: the features below
@@ -37,12 +37,13 @@
 // column per layer; each layer's W0 is stored shifted by l rows ("main", K = 32) next to a K = 8
 // "correction" block whose rows multiply the new columns and a constant-one column that carries the
 // bias b0.  The main part of layer l+1 is issued as soon as layer l's last GEMM2 quarter has drained,
-// i.e. it runs under layer l's epilogue; only the 3-MMA correction waits for the new column.
+// i.e. it runs under layer l's epilogue; only the 2-MMA correction waits for the new column.
 //
-// GEMM2 is pipelined with E1 at quarter granularity: quarter q of h_lo goes to Q buffer q & 1, its
-// GEMM2 step runs while the epilogue computes quarter q + 1.
-// TMEM (512 columns), per tile t at column 256 t:  P (128: H, then h_hi in place) | Q (2 x 32: packed
-// FP16 [h_lo | h_hi] quarters) | O (64: GEMM2 accumulators).
+// GEMM2 is pipelined with E1 at quarter granularity: quarter q's operands replace its own 32 H columns, its
+// GEMM2 step runs while the epilogue computes quarter q + 1 (one mbarrier per quarter: the epilogue may run a
+// whole layer ahead of the MMA warp, never two phases of one barrier).
+// TMEM (512 columns), per tile t at column 256 t:  P (128: H, then per 16-column chunk 8 columns of packed lo
+// pairs + 8 of packed hs pairs) | 64 unused | O (64: GEMM2 accumulators).
 #include <math.h>
 #include <string.h>
 
@@ -78,12 +79,12 @@ constexpr int SM_TOTAL = SM_MISC + 256;
 
 // barrier indices (8 bytes each); per-tile barriers are indexed + tile
 enum {
-  B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = 18, B_A2 = 20 /* [buf][tile] */, B_QFREE = 24 /* [buf][tile] */,
+  B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = 18, B_A2 = 20 /* [quarter][tile], one phase per layer */,
   B_OFULL = 28, B_COUNT = 30
 };
 
 // TMEM columns (per tile: + 256 * tile)
-constexpr uint32_t TM_P = 0, TM_Q = 128, TM_O = 192, TM_TILE = 256;
+constexpr uint32_t TM_P = 0, TM_O = 192, TM_TILE = 256;
 
 struct Params {
   const uint8_t* image;   // weight image: chunks of SLOT_BYTES in consumption order
@@ -164,16 +165,6 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdes
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -379,21 +370,33 @@ __device__ __forceinline__ void load_row<double>(const double* __restrict__ x, l
 // then sit at the magnitude of a_lo / w_hi, well inside the normal half range (unscaled, w_lo of a typical
 // 0.03 weight is a subnormal half and costs ~1e-6 relative per product).
 constexpr float HI_SCALE = 4.8828125e-4f;
+// GEMM2 runs entirely as kind::f16: one FP16 MMA covers K = 16 at the same ~45-cycle cost as a TF32 MMA
+// covering K = 8 (profiles/r1_mma_probe.txt), and an 11-bit significand is all the main term needs.
+// Compensated split of h:  hs = fp16(h * 2^-11) (round to nearest),  lo = h - 2^11 * float(hs)  (exact in
+// float32, whatever hs lost to rounding or to the half subnormal range), stored as fp16(lo).  Then
+//   h . w  ~=  hs . (w_hi * 2^11)  +  hs . (w_lo * 2^11)  +  lo . w_hi       (the lo . w_lo term, <= 2^-22, dropped)
+// with all products exact in the tensor core.  hs is a normal half for |h| in [0.125, 1.3e8]; below that lo
+// carries the remainder (|lo| <= 6e-5, absolute error <= 3e-8).  Beyond 1.3e8 the halves saturate.
+constexpr float H2_SCALE = 4.8828125e-4f;  // 2^-11
+constexpr float H2_INV = 2048.0f;
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {  // {low half, high half}
+  float2 r;
+  asm("{.reg .b16 a, b; mov.b32 {a, b}, %2; cvt.f32.f16 %0, a; cvt.f32.f16 %1, b;}" : "=f"(r.x), "=f"(r.y) : "r"(v));
+  return r;
+}
 
-// E1 for one 16-column chunk: h = leaky_relu(H) -> v: hi (top 19 bits, TF32) in place; wl / wh: the
-// kind::f16 correction operand, 8 words of packed lo pairs and 8 words of packed scaled hi pairs.
-// The bias b0 is already inside H (constant-one column of the A operand).
-__device__ __forceinline__ void e1_chunk(uint32_t (&v)[16], uint32_t (&wl)[8], uint32_t (&wh)[8]) {
+// E1 for one 16-column chunk: h = leaky_relu(H) -> wh: 8 words of packed hs pairs, wl: 8 words of packed lo pairs
+// (the compensated split above).  The bias b0 is already inside H (constant-one column of the A operand).
+__device__ __forceinline__ void e1_chunk(const uint32_t (&v)[16], uint32_t (&wl)[8], uint32_t (&wh)[8]) {
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
     float h0 = __uint_as_float(v[2 * jj]), h1 = __uint_as_float(v[2 * jj + 1]);
     h0 = fmaxf(h0, 0.01f * h0);
     h1 = fmaxf(h1, 0.01f * h1);
-    const uint32_t b0 = __float_as_uint(h0) & 0xffffe000u, b1 = __float_as_uint(h1) & 0xffffe000u;
-    v[2 * jj] = b0;
-    v[2 * jj + 1] = b1;
-    wl[jj] = pack_f16x2(h1 - __uint_as_float(b1), h0 - __uint_as_float(b0));
-    wh[jj] = pack_f16x2(__uint_as_float(b1) * HI_SCALE, __uint_as_float(b0) * HI_SCALE);
+    const uint32_t hs = pack_f16x2(h1 * H2_SCALE, h0 * H2_SCALE);
+    const float2 u = unpack_f16x2(hs);
+    wh[jj] = hs;
+    wl[jj] = pack_f16x2(fmaf(u.y, -H2_INV, h1), fmaf(u.x, -H2_INV, h0));
   }
 }
 
@@ -435,10 +438,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     for (int t = 0; t < NWG; ++t) {
       mbar_init(BAR(B_A1FULL + t), 128);
       mbar_init(BAR(B_HFULL + t), 1);
-      mbar_init(BAR(B_A2 + t), 128);
-      mbar_init(BAR(B_A2 + 2 + t), 128);
-      mbar_init(BAR(B_QFREE + t), 1);
-      mbar_init(BAR(B_QFREE + 2 + t), 1);
+      for (int q = 0; q < 4; ++q) mbar_init(BAR(B_A2 + 2 * q + t), 128);
       mbar_init(BAR(B_OFULL + t), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -483,7 +483,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     // released when both warps have committed on it (WEMPTY expects two arrivals).
     const int t = warp - 9;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
-    const uint32_t id128 = make_idesc(128), id64 = make_idesc(64), id32 = make_idesc(32);
+    const uint32_t id128 = make_idesc(128);
     const uint32_t ih128 = make_idesc_f16(128), ih64 = make_idesc_f16(64), ih32 = make_idesc_f16(32);
     const uint32_t a_x = sbase + SM_A1 + t * A_TILE;           // TF32 block: raw features, K-chunks 0..7
     const uint32_t a_new = a_x + 8 * 2048;                      // TF32 block: new columns + constant one
@@ -542,27 +542,32 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         // ---- GEMM2: four K = 32 quarters, each as soon as its half of E1 has landed
         const uint32_t n2 = scaled ? 64u : 32u;
         const uint32_t lbo2 = n2 * 16u;
-        const uint32_t qbytes = 8 * lbo2;  // one quarter of hi (or lo): 8 K-chunks
+        const uint32_t qbytes = 12 * lbo2;  // one quarter's weight block: 12 K'-chunks of 8 halves
         const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
-        const uint32_t id2 = scaled ? id64 : id32, ih2 = scaled ? ih64 : ih32;
+        const uint32_t ih2 = scaled ? ih64 : ih32;
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           const uint32_t gw = g + 3 + (scaled ? q : (q >> 1));
-          mbar_wait(BAR(B_A2 + 2 * (q & 1) + t), (uint32_t)(q >> 1));
+          // (one barrier per quarter: with two phases per layer on one barrier the epilogue, no longer held back by
+          // a Q-buffer hand-back, could complete both before this warp has seen the first)
+          mbar_wait(BAR(B_A2 + 2 * q + t), par);
           TR(22 + q);
           wwait(gw);
           tc_fence_after();
-          const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? 2 * qbytes : 0);
-          // quarter block in the chunk: TF32 hi [N2 x 32] | FP16 [N2 x 64 K'] (same byte size)
-          const uint64_t bd_hi = make_desc(wbase, lbo2, 128), bd_f16 = make_desc(wbase + qbytes, lbo2, 128);
-          const uint32_t a_f16 = tb + TM_Q + 32 * (q & 1), a_hi = tb + TM_P + 32 * q;
+          // quarter block in the chunk: FP16 [N2 x 96 K']: K' 0-31 w_hi (meets lo), 32-63 w_lo * 2^11 and
+          // 64-95 w_hi * 2^11 (both meet the scaled hi block).  Chunk c = 2 q + half holds its operands in
+          // place of its 16 H columns: 8 columns of packed lo pairs, 8 of packed scaled hi pairs.
+          const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? qbytes : 0);
+          const uint64_t bd = make_desc(wbase, lbo2, 128);
+          const uint32_t a0 = tb + TM_P + 32 * q;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_ts_f16(tb + TM_O, a_f16 + k * 8, bd_f16 + (uint64_t)k * kstep2, ih2, (q | k) ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ts(tb + TM_O, a_hi + k * 8, bd_hi + (uint64_t)k * kstep2, id2, 1);
-            tc_commit(BAR(B_QFREE + 2 * (q & 1) + t));
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t a_lo = a0 + 16 * half, a_hs = a_lo + 8;
+              mma_ts_f16(tb + TM_O, a_lo, bd + (uint64_t)half * kstep2, ih2, (q | half) ? 1u : 0u);
+              mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(2 + half) * kstep2, ih2, 1);
+              mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(4 + half) * kstep2, ih2, 1);
+            }
             if (q == 3) tc_commit(BAR(B_OFULL + t));
             if (scaled || (q & 1)) tc_commit(BAR(B_WEMPTY + (gw & (NSLOTS - 1))));
           }
@@ -586,7 +591,6 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     const int tid = threadIdx.x & 127;     // TMEM lane == sample row within the tile
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     const uint32_t tm_p = tmem_base + lane_base + wg * TM_TILE + TM_P;
-    const uint32_t tm_q = tmem_base + lane_base + wg * TM_TILE + TM_Q;
     const uint32_t tm_o = tmem_base + lane_base + wg * TM_TILE + TM_O;
     uint8_t* a1 = smem + SM_A1 + wg * A_TILE;
     double* scratch = reinterpret_cast<double*>(smem + SM_MISC + 16) + wg * 12;
@@ -658,7 +662,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         mbar_arrive(BAR(B_A1FULL + wg));
         TR(2);
         // ---- E1 in eight 16-column chunks, software pipelined: chunk c + 1 is in flight from TMEM while
-        // chunk c is computed.  Chunks 2q, 2q + 1 form quarter q: its FP16 operand goes to Q buffer q & 1 and
+        // chunk c is computed.  Chunks 2q, 2q + 1 form quarter q: its FP16 operands replace its H columns and
         // its GEMM2 step runs under the following chunks.
         mbar_wait(BAR(B_HFULL + wg), par);
         tc_fence_after();
@@ -675,17 +679,12 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             if (c < 7) tmem_ld16(tm_p + (c + 1) * 16, nxt);
             uint32_t wl[8], wh[8];
             e1_chunk(cur, wl, wh);
-            tmem_st16(tm_p + c * 16, cur);
-            if (c == 4 || c == 6) {  // Q buffer q & 1 is still GEMM2 quarter q - 2's operand until then
-              mbar_wait(BAR(B_QFREE + 2 * (q & 1) + wg), 0);
-              tc_fence_after();
-            }
-            tmem_st8(tm_q + (q & 1) * 32 + (c & 1) * 8, wl);
-            tmem_st8(tm_q + (q & 1) * 32 + 16 + (c & 1) * 8, wh);
+            tmem_st8(tm_p + c * 16, wl);      // in place of the chunk's own H columns (already in registers)
+            tmem_st8(tm_p + c * 16 + 8, wh);
             if (c & 1) {
               tmem_st_wait();
               tc_fence_before();
-              mbar_arrive(BAR(B_A2 + 2 * (q & 1) + wg));
+              mbar_arrive(BAR(B_A2 + 2 * q + wg));
               TR(4 + q);
             }
           }
@@ -844,6 +843,13 @@ int realnvp_tc_prepare(Flow* f) {
   const int nl = f->nlayers;
   if (nl > tc::MAX_TC_LAYERS) return HB_OK;
   const int d = f->d, u = f->u;
+  // GEMM2 weights are stored * 2^11 as halves: |w| must stay below 65504 / 2048 (else the CUDA-core path runs)
+  for (int l = 0; l < nl; ++l) {
+    const float* Wt = f->host_weights.data() + f->layer_off[l] + (size_t)d * 128 + 128;
+    const size_t n2 = (size_t)128 * u * ((l < ds.n_scaled) ? 2 : 1) + u;  // Wt, bt, (Ws): bt is harmless to include
+    for (size_t i = 0; i < n2; ++i)
+      if (!(fabsf(Wt[i]) < 16.0f)) return HB_OK;
+  }
   const size_t CF = tc::SLOT_BYTES / 4;  // floats per chunk
   size_t nchunks = 0;
   for (int l = 0; l < nl; ++l) nchunks += (l < ds.n_scaled) ? 7 : 5;
@@ -883,17 +889,24 @@ int realnvp_tc_prepare(Flow* f) {
           put_weight(v, c, kmajor_off(128, n, k), ch16, kmajor_off16(128, n, k), kmajor_off16(128, n, 8 + k));
         }
     }
-    // GEMM2: B[n][k] = [Wt | Ws][k][n]; one K = 32 quarter = TF32 hi block | FP16 block [N2 x 64 K']
+    // GEMM2: B[n][k] = [Wt | Ws][k][n]; one K = 32 quarter = FP16 block [N2 x 96 K']: K' < 32 fp16(w_hi) (meets
+    // lo), 32..63 fp16(w_lo * 2^11), 64..95 fp16(w_hi * 2^11) (both meet hs = fp16(h * 2^-11)).  12 K'-chunks of 8 halves:
+    // 192 N2 bytes per quarter, one quarter per 16 KiB slot for scaled layers, two for unscaled ones.
     const int N2 = scaled ? 64 : 32;
-    const size_t qf = (size_t)8 * N2 * 4;  // floats per quarter block (8 K-chunks)
+    const size_t qh = (size_t)12 * N2 * 8;  // halves per quarter block
     for (int q = 0; q < 4; ++q) {
-      float* c = scaled ? img.data() + (ch + 3 + q) * CF : img.data() + (ch + 3 + (q >> 1)) * CF + (q & 1) * 2 * qf;
-      uint16_t* c16 = reinterpret_cast<uint16_t*>(c + qf);
+      uint16_t* c16 = reinterpret_cast<uint16_t*>(scaled ? img.data() + (ch + 3 + q) * CF
+                                                         : img.data() + (ch + 3 + (q >> 1)) * CF) +
+                      ((!scaled && (q & 1)) ? qh : 0);
       for (int kk = 0; kk < 32; ++kk)
         for (int n = 0; n < N2; ++n) {
           const int k = 32 * q + kk;
           const float v = (n < u) ? Wt[(size_t)k * u + n] : Ws[(size_t)k * u + (n - u)];
-          put_weight(v, c, kmajor_off(N2, n, kk), c16, kmajor_off16(N2, n, kk), kmajor_off16(N2, n, 32 + kk));
+          float hi, lo;
+          split_tf32(v, &hi, &lo);
+          c16[kmajor_off16(N2, n, kk)] = f32_to_f16(hi);
+          c16[kmajor_off16(N2, n, 32 + kk)] = f32_to_f16(lo * 2048.0f);
+          c16[kmajor_off16(N2, n, 64 + kk)] = f32_to_f16(hi * 2048.0f);
         }
     }
     ch += scaled ? 7 : 5;
