@@ -45,6 +45,7 @@
 // TMEM (512 columns), per tile t at column 256 t:  P (128: H, then per 16-column chunk 8 columns of packed lo
 // pairs + 8 of packed hs pairs) | 64 unused | O (64: GEMM2 accumulators).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -59,32 +60,38 @@ constexpr int D = 64;
 constexpr int DH = 32;        // d = conditioning width (round(D/2))
 constexpr int U = 32;         // transformed width
 constexpr int TILE = 128;
-constexpr int NWG = 2;        // epilogue warpgroups = tiles in flight
-constexpr int THREADS = NWG * 128 + 96;  // + producer warp + one MMA warp per tile
 constexpr int SLOT_BYTES = 16384;
-constexpr int NSLOTS = 8;
 constexpr int MAX_TC_LAYERS = 8;  // one K = 8 correction step holds 7 new columns + the bias column
 constexpr int KA = 40;            // A operand columns: 32 raw + 7 new + 1 constant
 constexpr int A_HALF = KA / 4 * 2048;  // bytes of the hi (or lo) half of a tile's A operand
 constexpr int A_TILE = 2 * A_HALF;
 
-// shared memory carve-up (bytes)
-constexpr int SM_RING = 0;
-constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;       // per tile: hi | lo
-constexpr int SM_BIAS = SM_A1 + NWG * A_TILE;              // b2: MAX_TC_LAYERS * 64 floats
-constexpr int SM_PRE = SM_BIAS + MAX_TC_LAYERS * 64 * 4;   // standardisation: inv_amp[D], -offset*inv_amp[D]
-constexpr int SM_BAR = SM_PRE + 2 * D * 4;                 // mbarriers
-constexpr int SM_MISC = SM_BAR + 512;                      // tmem ptr, fold scratch
-constexpr int SM_TOTAL = SM_MISC + 256;
-
-// barrier indices (8 bytes each); per-tile barriers are indexed + tile
-enum {
-  B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = 18, B_A2 = 20 /* [quarter][tile], one phase per layer */,
-  B_OFULL = 28, B_COUNT = 30
+// Layout for NT tiles (= epilogue warpgroups) in flight per CTA.
+//   NT = 2: TMEM per tile P 128 | 64 unused | O 64; 8 weight slots; y[64] per thread with a register rotation
+//   NT = 3: TMEM per tile P 128 | O 32 (480 of 512 columns): scaled layers run GEMM2 in TWO N = 32 passes over the
+//           same h operands (shift, then scale, see the kernel); 6 weight slots; 128 registers per thread, so the
+//           epilogue keeps only the 32 transformed features + the 7 that can enter (owned by ORIGINAL index)
+template <int NT>
+struct L {
+  static constexpr int NSLOTS = NT == 3 ? 6 : 8;
+  static constexpr int THREADS = NT * 128 + 32 * (NT + 1);  // + producer warp + one MMA warp per tile
+  // shared memory carve-up (bytes)
+  static constexpr int SM_RING = 0;
+  static constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;       // per tile: hi | lo
+  static constexpr int SM_BIAS = SM_A1 + NT * A_TILE;               // b2: MAX_TC_LAYERS * 64 floats
+  static constexpr int SM_PRE = SM_BIAS + MAX_TC_LAYERS * 64 * 4;   // standardisation: inv_amp[D], -offset*inv_amp[D]
+  static constexpr int SM_BAR = SM_PRE + 2 * D * 4;                 // mbarriers
+  static constexpr int SM_MISC = SM_BAR + 512;                      // tmem ptr, fold scratch
+  static constexpr int SM_TOTAL = SM_MISC + 512;
+  // barrier indices (8 bytes each); per-tile barriers are indexed + tile
+  static constexpr int B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = B_A1FULL + NT,
+                       B_A2 = B_HFULL + NT /* [quarter][tile], one phase per layer */, B_OFULL = B_A2 + 4 * NT,
+                       B_OCONS = B_OFULL + NT /* NT = 3: shift pass read, O may be overwritten */,
+                       B_OFULL2 = B_OCONS + NT /* NT = 3: scale pass complete */, B_COUNT = B_OFULL2 + NT;
+  static_assert(B_COUNT * 8 <= 512, "barrier block");
+  // TMEM columns (per tile: + TM_TILE * tile)
+  static constexpr uint32_t TM_P = 0, TM_O = NT == 3 ? 128 : 192, TM_TILE = NT == 3 ? 160 : 256;
 };
-
-// TMEM columns (per tile: + 256 * tile)
-constexpr uint32_t TM_P = 0, TM_O = 192, TM_TILE = 256;
 
 struct Params {
   const uint8_t* image;   // weight image: chunks of SLOT_BYTES in consumption order
@@ -237,6 +244,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 // wait::ld that also names the registers of the load it completes: a prefetched chunk's values cannot be
 // consumed (or moved by the compiler) ahead of the wait
@@ -402,11 +415,20 @@ __device__ __forceinline__ void e1_chunk(const uint32_t (&v)[16], uint32_t (&wl)
 
 __device__ __forceinline__ int layer_chunks(bool scaled) { return scaled ? 7 : 5; }
 
-template <typename XT, typename LT, bool FOLD>
-__global__ void __launch_bounds__(THREADS, 1)
+template <typename XT, typename LT, bool FOLD, int NT>
+__global__ void __launch_bounds__(L<NT>::THREADS, 1)
 realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __restrict__ lnpost,
                   float* __restrict__ lnpred_out, FoldParams fp) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  using C = L<NT>;
+  constexpr int NWG = NT, THREADS = C::THREADS, NSLOTS = C::NSLOTS;
+  constexpr int SM_RING = C::SM_RING, SM_A1 = C::SM_A1, SM_BIAS = C::SM_BIAS, SM_PRE = C::SM_PRE, SM_BAR = C::SM_BAR,
+                SM_MISC = C::SM_MISC;
+  constexpr int B_WFULL = C::B_WFULL, B_WEMPTY = C::B_WEMPTY, B_A1FULL = C::B_A1FULL, B_HFULL = C::B_HFULL,
+                B_A2 = C::B_A2, B_OFULL = C::B_OFULL, B_OCONS = C::B_OCONS, B_OFULL2 = C::B_OFULL2;
+  constexpr uint32_t TM_P = C::TM_P, TM_O = C::TM_O, TM_TILE = C::TM_TILE;
+  constexpr int W_PROD = 4 * NT, W_MMA = W_PROD + 1;  // weight producer warp; the MMA warps follow
+  (void)B_OCONS; (void)B_OFULL2;
   // lane-0 broadcast: tells the compiler the warp index (and with it the role dispatch below) is
   // warp-uniform, so the MMA warps' addresses, descriptors and loop state live on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -424,8 +446,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   const bool tr_on = blockIdx.x == 0 && lane == 0 && warp < 4;
   const int tr_s = warp;
 #else
-  const bool tr_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp >= 9);
-  const int tr_s = warp == 0 ? 0 : warp == 4 ? 1 : warp == 9 ? 2 : 3;
+  const bool tr_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == W_MMA || warp == W_MMA + 1);
+  const int tr_s = warp == 0 ? 0 : warp == 4 ? 1 : warp == W_MMA ? 2 : 3;
 #endif
 #endif
 
@@ -438,8 +460,10 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     for (int t = 0; t < NWG; ++t) {
       mbar_init(BAR(B_A1FULL + t), 128);
       mbar_init(BAR(B_HFULL + t), 1);
-      for (int q = 0; q < 4; ++q) mbar_init(BAR(B_A2 + 2 * q + t), 128);
+      for (int q = 0; q < 4; ++q) mbar_init(BAR(B_A2 + NT * q + t), 128);
       mbar_init(BAR(B_OFULL + t), 1);
+      mbar_init(BAR(B_OCONS + t), 128);
+      mbar_init(BAR(B_OFULL2 + t), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -449,7 +473,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     pre_s[i] = inv;
     pre_s[D + i] = P.pre ? -P.pre[i] * inv : 0.f;
   }
-  if (warp == 9) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void*)tmem_ptr)),
                  "r"(512u)
@@ -461,14 +485,14 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == W_PROD) {
     // ===== weight producer: the image is one batch worth of chunks, replayed every batch =====
     if (lane == 0) {
       uint32_t g = 0;
       for (int b = 0; b < P.nbatches; ++b) {
         const uint8_t* src = P.image;
         for (int c = 0; c < P.chunks_per_batch; ++c, ++g) {
-          const uint32_t slot = g & (NSLOTS - 1), use = g / NSLOTS;
+          const uint32_t slot = g % NSLOTS, use = g / NSLOTS;
           mbar_wait(BAR(B_WEMPTY + slot), (use & 1) ^ 1);
           mbar_expect_tx(BAR(B_WFULL + slot), SLOT_BYTES);
           bulk_g2s(sbase + SM_RING + slot * SLOT_BYTES, src, SLOT_BYTES, BAR(B_WFULL + slot));
@@ -476,12 +500,12 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         }
       }
     }
-  } else if (warp >= 9) {
+  } else if (warp >= W_MMA) {
     // ===== MMA issuers: warp 9 serves tile 0, warp 10 tile 1.  Each runs a straight-line program
     // per layer with blocking mbarrier waits; the whole warp executes it (warp-uniform, so the
     // descriptors stay in uniform registers) and one elected lane issues.  A weight slot is
     // released when both warps have committed on it (WEMPTY expects two arrivals).
-    const int t = warp - 9;
+    const int t = warp - W_MMA;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
     const uint32_t id128 = make_idesc(128);
     const uint32_t ih128 = make_idesc_f16(128), ih64 = make_idesc_f16(64), ih32 = make_idesc_f16(32);
@@ -491,11 +515,11 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     const uint64_t adx_hi = make_desc(a_x, 2048, 128), adx_f16 = make_desc(a_h, 2048, 128);
     const uint64_t adn_hi = make_desc(a_new, 2048, 128), adn_f16 = make_desc(a_h + 8 * 2048, 2048, 128);
     auto wwait = [&](uint32_t gidx) {
-      mbar_wait(BAR(B_WFULL + (gidx & (NSLOTS - 1))), (gidx / NSLOTS) & 1);
+      mbar_wait(BAR(B_WFULL + (gidx % NSLOTS)), (gidx / NSLOTS) & 1);
     };
-    auto chunk_addr = [&](uint32_t gidx) { return sbase + SM_RING + (gidx & (NSLOTS - 1)) * SLOT_BYTES; };
+    auto chunk_addr = [&](uint32_t gidx) { return sbase + SM_RING + (gidx % NSLOTS) * SLOT_BYTES; };
     auto release = [&](uint32_t gidx) {
-      if (elect_one()) tc_commit(BAR(B_WEMPTY + (gidx & (NSLOTS - 1))));
+      if (elect_one()) tc_commit(BAR(B_WEMPTY + (gidx % NSLOTS)));
       __syncwarp();
     };
     // main part of GEMM1: H = x(0..31) . W0main.  Chunk g+1 = FP16 correction operand [128 x 64 K'],
@@ -515,7 +539,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       }
       __syncwarp();
     };
-    uint32_t g = 0, it = 0;
+    uint32_t g = 0, it = 0, sc_it = 0;
+    (void)sc_it;
     for (int b = 0; b < P.nbatches; ++b) {
       for (int l = 0; l < nl; ++l, ++it) {
         const bool scaled = l < P.nscaled;
@@ -532,9 +557,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             mma_ss_f16(tb + TM_P, adn_f16, wc + (uint64_t)(4096 >> 4), ih128, 1);  // K' = 16: [lo new | hi new]
             mma_ss(tb + TM_P, adn_hi, wc, id128, 1);                               // K = 8 TF32
             tc_commit(BAR(B_HFULL + t));
-            tc_commit(BAR(B_WEMPTY + (g & (NSLOTS - 1))));
-            tc_commit(BAR(B_WEMPTY + ((g + 1) & (NSLOTS - 1))));
-            tc_commit(BAR(B_WEMPTY + ((g + 2) & (NSLOTS - 1))));
+            tc_commit(BAR(B_WEMPTY + (g % NSLOTS)));
+            tc_commit(BAR(B_WEMPTY + ((g + 1) % NSLOTS)));
+            tc_commit(BAR(B_WEMPTY + ((g + 2) % NSLOTS)));
           }
           __syncwarp();
           TR(21);
@@ -544,13 +569,15 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         const uint32_t lbo2 = n2 * 16u;
         const uint32_t qbytes = 12 * lbo2;  // one quarter's weight block: 12 K'-chunks of 8 halves
         const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
-        const uint32_t ih2 = scaled ? ih64 : ih32;
+        // NT = 3: O holds 32 columns, scaled layers take the shift rows (0..31 of the block) in this pass
+        const bool two_pass = NT == 3 && scaled;
+        const uint32_t ih2 = (scaled && NT != 3) ? ih64 : ih32;
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           const uint32_t gw = g + 3 + (scaled ? q : (q >> 1));
           // (one barrier per quarter: with two phases per layer on one barrier the epilogue, no longer held back by
           // a Q-buffer hand-back, could complete both before this warp has seen the first)
-          mbar_wait(BAR(B_A2 + 2 * q + t), par);
+          mbar_wait(BAR(B_A2 + NT * q + t), par);
           TR(22 + q);
           wwait(gw);
           tc_fence_after();
@@ -569,23 +596,50 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
               mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(4 + half) * kstep2, ih2, 1);
             }
             if (q == 3) tc_commit(BAR(B_OFULL + t));
-            if (scaled || (q & 1)) tc_commit(BAR(B_WEMPTY + (gw & (NSLOTS - 1))));
+            if (!two_pass && (scaled || (q & 1))) tc_commit(BAR(B_WEMPTY + (gw % NSLOTS)));
           }
           __syncwarp();
           TR(26 + q);
+        }
+        if constexpr (NT == 3) {
+          if (scaled) {
+            // ---- second pass: the scale rows (32..63 of each quarter block, + 4 row groups of 128 bytes) over the
+            // same h operands, into the same 32 O columns once the epilogue has read the shifts out of them
+            mbar_wait(BAR(B_OCONS + t), sc_it & 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll 1
+              for (int q = 0; q < 4; ++q) {
+                const uint64_t bd = make_desc(chunk_addr(g + 3 + q) + 512, lbo2, 128);
+                const uint32_t a0 = tb + TM_P + 32 * q;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const uint32_t a_lo = a0 + 16 * half, a_hs = a_lo + 8;
+                  mma_ts_f16(tb + TM_O, a_lo, bd + (uint64_t)half * kstep2, ih32, (q | half) ? 1u : 0u);
+                  mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(2 + half) * kstep2, ih32, 1);
+                  mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(4 + half) * kstep2, ih32, 1);
+                }
+                tc_commit(BAR(B_WEMPTY + ((g + 3 + q) % NSLOTS)));
+              }
+              tc_commit(BAR(B_OFULL2 + t));
+            }
+            __syncwarp();
+          }
         }
         g += layer_chunks(scaled);
         // ---- early main part of the next layer: runs under this layer's E2.  P is GEMM2's A operand
         // until the last quarter has drained.
         if (l + 1 < nl) {
-          mbar_wait(BAR(B_OFULL + t), par);
+          if (two_pass) mbar_wait(BAR(B_OFULL2 + t), sc_it & 1);
+          else mbar_wait(BAR(B_OFULL + t), par);
           TR(30);
           issue_main(g);
           TR(31);
         }
+        if (two_pass) ++sc_it;
       }
     }
-  } else {
+  } else if constexpr (NT == 2) {
     // ===== epilogue warpgroups =====
     const int wg = warp >> 2;              // 0 / 1
     const int tid = threadIdx.x & 127;     // TMEM lane == sample row within the tile
@@ -684,7 +738,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             if (c & 1) {
               tmem_st_wait();
               tc_fence_before();
-              mbar_arrive(BAR(B_A2 + 2 * q + wg));
+              mbar_arrive(BAR(B_A2 + NT * q + wg));
               TR(4 + q);
             }
           }
@@ -754,6 +808,221 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       }
     }
     if (FOLD) fold.finish(had_rows);
+  } else {
+    // ===== epilogue warpgroups, NT = 3 =====
+    // 128 registers per thread: features are owned by ORIGINAL index and nothing rotates.  yt[i] = feature 32 + i,
+    // x7[i] = feature i < 7 (feature i joins the transformed half from layer i + 1 on); the features that no layer
+    // touches (7..31) only contribute their squares, summed at the tile start.  At layer l feature f is GEMM2 output
+    // column k = (f - 32 - l) mod 64, so O is read at a column offset of -l: entry i of the 32-column load is
+    // feature 32 + i for i >= l (below that the feature is frozen and the word -- whatever lies left of O -- is
+    // discarded); features i < l sit at columns 32 - l + i.  Scaled layers: O receives the shifts, then (second
+    // MMA pass, after OCONS) the scale pre-activations.
+    const int wg = warp >> 2;              // 0..2 = tile
+    const int tid = threadIdx.x & 127;     // TMEM lane == sample row within the tile
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    const uint32_t tm_p = tmem_base + lane_base + wg * TM_TILE + TM_P;
+    const uint32_t tm_o = tmem_base + lane_base + wg * TM_TILE + TM_O;
+    uint8_t* a1 = smem + SM_A1 + wg * A_TILE;
+    double* scratch = reinterpret_cast<double*>(smem + SM_MISC + 16) + wg * 12;
+    const int flusher = blockIdx.x * NWG + wg;
+    const long long row_lo = (long long)flusher * P.rows_per_wg;
+    long long row_hi = row_lo + P.rows_per_wg;
+    if (row_hi > P.nrows) row_hi = P.nrows;
+    const bool had_rows = row_lo < P.nrows;
+    Fold<128> fold(fp, flusher, tid, scratch, (FOLD && had_rows) ? row_lo : 0, 1 + wg);  // named barriers 1..3
+    const float invT = 1.f / P.T;
+    const float base_const = -(float)D * logf(P.T) - 0.5f * (float)D * 1.8378770664093453f;
+    constexpr int NX = MAX_TC_LAYERS - 1;  // features that can enter the transformed half
+    uint32_t it = 0, sc_it = 0;
+
+    for (int b = 0; b < P.nbatches; ++b) {
+      const long long t0 = row_lo + (long long)b * TILE;
+      const long long r = t0 + tid;
+      const bool live = r < row_hi;
+      const long long rr = live ? r : 0;
+      float yt[U], x7[NX], ss = 0.f;
+      TR(1);
+      {
+        float y[D];
+        load_row<XT>(x, ld, rr, y);
+        if (r + TILE < row_hi) {  // pull the next tile's row into L2 while this tile computes
+          const char* nx = reinterpret_cast<const char*>(x + (r + TILE) * ld);
+#pragma unroll
+          for (int q = 0; q < (int)(D * sizeof(XT)); q += 128) prefetch_l2(nx + q);
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
+        // A operand, written once per tile (layout as in the NT = 2 branch)
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          uint4 hi0, hi1, plo, phi;
+          uint32_t* p0 = &hi0.x;
+          uint32_t* p1 = &hi1.x;
+          uint32_t* ql = &plo.x;
+          uint32_t* qh = &phi.x;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float va = y[8 * c + 2 * q], vb = y[8 * c + 2 * q + 1];
+            const uint32_t ha = __float_as_uint(va) & 0xffffe000u, hb = __float_as_uint(vb) & 0xffffe000u;
+            (q < 2 ? p0 : p1)[(2 * q) & 3] = ha;
+            (q < 2 ? p0 : p1)[(2 * q + 1) & 3] = hb;
+            ql[q] = pack_f16x2(vb - __uint_as_float(hb), va - __uint_as_float(ha));
+            qh[q] = pack_f16x2(__uint_as_float(hb) * HI_SCALE, __uint_as_float(ha) * HI_SCALE);
+          }
+          *reinterpret_cast<uint4*>(a1 + (2 * c) * 2048 + tid * 16) = hi0;
+          *reinterpret_cast<uint4*>(a1 + (2 * c + 1) * 2048 + tid * 16) = hi1;
+          *reinterpret_cast<uint4*>(a1 + A_HALF + c * 2048 + tid * 16) = plo;
+          *reinterpret_cast<uint4*>(a1 + A_HALF + (4 + c) * 2048 + tid * 16) = phi;
+        }
+        {
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = z;
+          *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x3f800000u);
+          *reinterpret_cast<uint4*>(a1 + A_HALF + 8 * 2048 + tid * 16) = z;
+          *reinterpret_cast<uint4*>(a1 + A_HALF + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x10000000u);
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x7[i] = y[i];
+#pragma unroll
+        for (int i = NX; i < DH; ++i) {
+          const float z = y[i] * invT;
+          ss = fmaf(z, z, ss);
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) yt[i] = y[DH + i];
+      }
+      float ldj = 0.f;
+      for (int l = 0; l < nl; ++l, ++it) {
+        const uint32_t par = it & 1;
+        const bool scaled = l < P.nscaled;
+        const float* bl = bias_s + l * 64 - l;  // bl[i] = bt[i - l], bl[32 + i] = bt[32 - l + i] = bs[i - l], bl[64 + i] = bs[32 - l + i]
+        fence_proxy_async();
+        tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
+        mbar_arrive(BAR(B_A1FULL + wg));
+        TR(2);
+        // ---- E1 (as in the NT = 2 branch)
+        mbar_wait(BAR(B_HFULL + wg), par);
+        tc_fence_after();
+        TR(3);
+        {
+          uint32_t va[16], vb[16];
+          tmem_ld16(tm_p, va);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t(&cur)[16] = (c & 1) ? vb : va;
+            uint32_t(&nxt)[16] = (c & 1) ? va : vb;
+            const int q = c >> 1;
+            tmem_ld_wait16(cur);
+            if (c < 7) tmem_ld16(tm_p + (c + 1) * 16, nxt);
+            uint32_t wl[8], wh[8];
+            e1_chunk(cur, wl, wh);
+            tmem_st8(tm_p + c * 16, wl);
+            tmem_st8(tm_p + c * 16 + 8, wh);
+            if (c & 1) {
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(BAR(B_A2 + NT * q + wg));
+              TR(4 + q);
+            }
+          }
+        }
+        // ---- E2, shifts
+        mbar_wait(BAR(B_OFULL + wg), par);
+        tc_fence_after();
+        TR(9);
+        {
+          uint32_t v0[U], v1[8];
+          tmem_ld32(tm_o - l, v0);
+          tmem_ld8(tm_o + U - l, v1);
+          tmem_ld_wait();
+          if (scaled) {  // the MMA warp may overwrite O with the scale pass
+            tc_fence_before();
+            mbar_arrive(BAR(B_OCONS + wg));
+          }
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const float shift = __uint_as_float(v0[i]) + bl[i];
+            yt[i] -= (i >= NX || i >= l) ? shift : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            const float shift = __uint_as_float(v1[i]) + bl[U + i];
+            x7[i] -= (i < l) ? shift : 0.f;
+          }
+        }
+        if (scaled) {
+          // ---- E2, scales: y /= clip(softplus(a)), ldj -= sum log scale
+          mbar_wait(BAR(B_OFULL2 + wg), sc_it & 1);
+          tc_fence_after();
+          ++sc_it;
+          uint32_t v0[U], v1[8];
+          tmem_ld32(tm_o - l, v0);
+          tmem_ld8(tm_o + U - l, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k0 = 0; k0 < U; k0 += 8) {
+            float prod = 1.f;  // 8 factors in [1e-3, 1e3] stay inside the float32 range
+#pragma unroll
+            for (int i = k0; i < k0 + 8; ++i) {
+              const bool act = i >= NX || i >= l;
+              const float a = __uint_as_float(v0[i]) + bl[U + i];
+              float sc = softplus_clip_fast(a);
+              sc = (a != a) ? a : sc;  // keep NaN (fminf/fmaxf would drop it)
+              const float yn = yt[i] * rcp_approx(sc);
+              yt[i] = act ? yn : yt[i];
+              prod *= act ? sc : 1.f;
+            }
+            ldj -= 0.6931471805599453f * lg2_approx(prod);
+          }
+          if (l > 0) {
+            float prod = 1.f;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+              if (i < l) {
+                const float a = __uint_as_float(v1[i]) + bl[2 * U + i];
+                float sc = softplus_clip_fast(a);
+                sc = (a != a) ? a : sc;
+                x7[i] *= rcp_approx(sc);
+                prod *= sc;
+              }
+            }
+            ldj -= 0.6931471805599453f * lg2_approx(prod);
+          }
+        }
+        if (l + 1 < nl) {
+          // feature 32 + l is final from here on: it is the new conditioning column l of the following layers
+          float v = yt[0];
+#pragma unroll
+          for (int i = 1; i < NX; ++i) v = (l == i) ? yt[i] : v;
+          const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
+          const int col = DH + l;
+          *reinterpret_cast<uint32_t*>(a1 + (col >> 2) * 2048 + tid * 16 + (col & 3) * 4) = hb;
+          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 8 * 2048 + tid * 16 + l * 2) = to_f16(v - __uint_as_float(hb));
+          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 9 * 2048 + tid * 16 + l * 2) = to_f16(__uint_as_float(hb) * HI_SCALE);
+        }
+        TR(10);
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const float z = yt[i] * invT;
+        ss = fmaf(z, z, ss);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const float z = x7[i] * invT;
+        ss = fmaf(z, z, ss);
+      }
+      const float lnphi = -0.5f * ss + base_const + ldj - P.sum_log_amp;
+      if (live && lnpred_out) lnpred_out[r] = lnphi;
+      if (FOLD) {
+        float a[1] = {lnphi};
+        float bb[1] = {live ? (float)lnpost[r] : 0.f};
+        long long t1 = t0 + TILE;
+        if (t1 > row_hi) t1 = row_hi;
+        if (t0 < row_hi) fold.tile<1>(t0, t1, a, bb);
+      }
+    }
+    if (FOLD) fold.finish(had_rows);
   }
 #ifdef HB_TC_TRACE
   if (tr_on) g_trace_n[tr_s] = tr_n;
@@ -762,7 +1031,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -928,12 +1197,27 @@ void realnvp_tc_release(Flow* f) {
   f->tc_image = nullptr;
 }
 
+// tiles in flight per CTA: HB_TC_TILES = 2 | 3 (A/B measurements)
+static int tc_tiles() {
+  static const int v = [] {
+    const char* e = getenv("HB_TC_TILES");
+    return (e && e[0] == '2') ? 2 : 3;
+  }();
+  return v;
+}
+
 template <typename XT, typename LT, bool FOLD>
 static int tc_launch(const tc::Params& P, int grid, const void* x, long long ld, const void* lnpost,
                      float* lnpred_out, const FoldParams& fp, cudaStream_t st) {
-  auto kern = tc::realnvp_tc_kernel<XT, LT, FOLD>;
-  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
-  kern<<<grid, tc::THREADS, tc::SM_TOTAL, st>>>(P, (const XT*)x, ld, (const LT*)lnpost, lnpred_out, fp);
+  if (tc_tiles() == 3) {
+    auto kern = tc::realnvp_tc_kernel<XT, LT, FOLD, 3>;
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::L<3>::SM_TOTAL));
+    kern<<<grid, tc::L<3>::THREADS, tc::L<3>::SM_TOTAL, st>>>(P, (const XT*)x, ld, (const LT*)lnpost, lnpred_out, fp);
+  } else {
+    auto kern = tc::realnvp_tc_kernel<XT, LT, FOLD, 2>;
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::L<2>::SM_TOTAL));
+    kern<<<grid, tc::L<2>::THREADS, tc::L<2>::SM_TOTAL, st>>>(P, (const XT*)x, ld, (const LT*)lnpost, lnpred_out, fp);
+  }
   return HB_OK;
 }
 
@@ -948,12 +1232,13 @@ int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, l
   if (n <= 0) return HB_OK;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-  long long nwg = (long long)sms * tc::NWG;
+  const int NWG = tc_tiles();
+  long long nwg = (long long)sms * NWG;
   long long rpw = (n + nwg - 1) / nwg;
   rpw = ((rpw + tc::TILE - 1) / tc::TILE) * tc::TILE;
   nwg = (n + rpw - 1) / rpw;
-  const int grid = (int)((nwg + tc::NWG - 1) / tc::NWG);
-  const long long nfl = (long long)grid * tc::NWG;
+  const int grid = (int)((nwg + NWG - 1) / NWG);
+  const long long nfl = (long long)grid * NWG;
   tc::Params P;
   P.image = static_cast<const uint8_t*>(f->tc_image);
   P.bias = reinterpret_cast<const float*>(static_cast<const char*>(f->tc_image) + f->tc_image_bytes);
