@@ -376,17 +376,18 @@ def main():
         peak = float(peaks["bf16_tflops"]) / 2.0
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None,
-                # ncu --set full (profiles/r1_prof_tc_r1h_raw_summary.csv): 262.8 B of DRAM traffic per sample
-                # (algorithmic 260 B): the kernel is not memory bound
-                "traffic": 263.0 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
+                # ncu --set full (profiles/r1_prof_tc_r1j_raw_summary.csv): 262.3 B of DRAM traffic per sample
+                # (read 260.4 + write 1.9; algorithmic 260 B): the kernel is not memory bound
+                "traffic": 262.3 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
                 "kernel": "realnvp_tc_kernel", "kernel_ms": kms,
                 "peak_source": "TF32 dense = bf16 burst / 2, of %s" % peak_kind,
                 # issued: 0.54x as kind::tf32 (GEMM1 main term, K 32 -> 40) + 2.79x as kind::f16 (GEMM1 corrections,
-                # all of GEMM2); a tcgen05.mma costs max(~45, N/2) cycles whatever its kind (profiles/r1_mma_probe.txt):
-                # 10 x 64.4 + 24 x 45 = 1724 tensor-pipe cycles per 128-sample tile and layer => pipe bound 29.5 ms
-                # for 1e8 samples at 1.85 GHz, i.e. frac <= 0.47 for this instruction mix
+                # all of GEMM2); a tcgen05.mma costs max(~45, N/2) cycles whatever its kind (profiles/r1_mma_probe.txt).
+                # Three tiles in flight leave 32 accumulator columns per tile, so the 2 scaled layers run GEMM2 in two
+                # N = 32 passes: 10 x 64.4 + (2 x 48 + 4 x 24)/6 x 45 = 2084 tensor-pipe cycles per 128-sample tile and
+                # layer => pipe bound 35.7 ms for 1e8 samples at 1.85 GHz, i.e. frac <= 0.39 for this instruction mix
                 "issued_mma_flop_factor": 3.32, "issued_tf32_time_factor": 1.93,
-                "mma_instructions_per_tile_layer": 34, "tensor_pipe_cycles_per_tile_layer": 1724,
+                "mma_instructions_per_tile_layer": 42, "tensor_pipe_cycles_per_tile_layer": 2084,
                 "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
     else:
         # small-ndim flows run on the FP32 CUDA cores (tensor tiles would be >= 75 % padding):

@@ -4,14 +4,15 @@
 // + harmonic/evidence.py:278-352 for the shapes the tensor path supports (ndim = 64, <= 8 coupling
 // layers; everything else runs on the CUDA-core kernels).
 //
-// Mapping.  One persistent CTA per SM, 352 threads:
-//   warps 0-3 / 4-7 : two epilogue warpgroups; each owns one 128-sample tile at a time, one sample
-//                     per thread (TMEM lane = sample), y[64] in registers through all layers
-//   warp 8          : weight producer: streams the pre-split weight image (TF32 hi + FP16 correction
-//                     blocks, UMMA canonical no-swizzle K-major layout, built once on the host) from L2
-//                     into an 8-slot ring
-//                     of 16 KiB chunks with cp.async.bulk + mbarrier
-//   warps 9, 10     : tcgen05.mma issuers, one per tile (warp 9 also allocates TMEM); warp-uniform
+// Mapping.  One persistent CTA per SM, NT 128-sample tiles in flight (template parameter; 3 by default,
+// HB_TC_TILES=2 selects the two-tile layout for A/B measurements), 128 NT + 32 (NT + 1) threads:
+//   NT epilogue warpgroups : each owns one tile at a time, one sample per thread (TMEM lane = sample).
+//                     NT = 3 (128 registers per thread): the 32 initially transformed features + the 7 that
+//                     can enter, owned by ORIGINAL index; NT = 2: y[64] with a register rotation per layer
+//   producer warp   : streams the pre-split weight image (TF32 hi + FP16 correction blocks, UMMA canonical
+//                     no-swizzle K-major layout, built once on the host) from L2 into a ring of 16 KiB
+//                     chunks (6 slots for NT = 3, 8 for NT = 2) with cp.async.bulk + mbarrier
+//   NT MMA warps    : tcgen05.mma issuers, one per tile (the first also allocates TMEM); warp-uniform
 //                     straight-line program with blocking mbarrier waits, one elected lane issues
 //
 // Per coupling layer and tile
@@ -42,8 +43,10 @@
 // GEMM2 is pipelined with E1 at quarter granularity: quarter q's operands replace its own 32 H columns, its
 // GEMM2 step runs while the epilogue computes quarter q + 1 (one mbarrier per quarter: the epilogue may run a
 // whole layer ahead of the MMA warp, never two phases of one barrier).
-// TMEM (512 columns), per tile t at column 256 t:  P (128: H, then per 16-column chunk 8 columns of packed lo
-// pairs + 8 of packed hs pairs) | 64 unused | O (64: GEMM2 accumulators).
+// TMEM, P = 128 columns per tile (H, then per 16-column chunk 8 columns of packed lo pairs + 8 of packed hs pairs):
+//   NT = 3: tile t at column 160 t: P | O (32).  Scaled layers run GEMM2 twice over the same h operands: the shift
+//           rows first, then -- once the epilogue has read the shifts out of O (OCONS) -- the scale rows (OFULL2)
+//   NT = 2: tile t at column 256 t: P | 64 unused | O (64: one GEMM2 pass, N = 64 on scaled layers).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
