@@ -376,7 +376,7 @@ def main():
         peak = float(peaks["bf16_tflops"]) / 2.0
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None,
-                # ncu --set full (profiles/r1_prof_tc_r1j_raw_summary.csv): 262.3 B of DRAM traffic per sample
+                # ncu --set full (profiles/r1_prof_tc_r1k_raw_summary.csv): 262.3 B of DRAM traffic per sample
                 # (read 260.4 + write 1.9; algorithmic 260 B): the kernel is not memory bound
                 "traffic": 262.3 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
                 "kernel": "realnvp_tc_kernel", "kernel_ms": kms,

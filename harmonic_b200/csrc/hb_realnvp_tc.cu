@@ -44,8 +44,9 @@
 // GEMM2 step runs while the epilogue computes quarter q + 1 (one mbarrier per quarter: the epilogue may run a
 // whole layer ahead of the MMA warp, never two phases of one barrier).
 // TMEM, P = 128 columns per tile (H, then per 16-column chunk 8 columns of packed lo pairs + 8 of packed hs pairs):
-//   NT = 3: tile t at column 160 t: P | O (32).  Scaled layers run GEMM2 twice over the same h operands: the shift
-//           rows first, then -- once the epilogue has read the shifts out of O (OCONS) -- the scale rows (OFULL2)
+//   NT = 3: tile t at column 160 t: P | O (32).  Scaled layers run GEMM2 twice over the same h operands: the scale
+//           rows first, then -- once the epilogue has read the pre-activations out of O (OCONS) -- the shift rows
+//           (OFULL2), which so run under the softplus / reciprocal / log-det arithmetic of the epilogue
 //   NT = 2: tile t at column 256 t: P | 64 unused | O (64: one GEMM2 pass, N = 64 on scaled layers).
 #include <math.h>
 #include <stdlib.h>
@@ -89,8 +90,8 @@ struct L {
   // barrier indices (8 bytes each); per-tile barriers are indexed + tile
   static constexpr int B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = B_A1FULL + NT,
                        B_A2 = B_HFULL + NT /* [quarter][tile], one phase per layer */, B_OFULL = B_A2 + 4 * NT,
-                       B_OCONS = B_OFULL + NT /* NT = 3: shift pass read, O may be overwritten */,
-                       B_OFULL2 = B_OCONS + NT /* NT = 3: scale pass complete */, B_COUNT = B_OFULL2 + NT;
+                       B_OCONS = B_OFULL + NT /* NT = 3: first pass read, O may be overwritten */,
+                       B_OFULL2 = B_OCONS + NT /* NT = 3: second (shift) pass complete */, B_COUNT = B_OFULL2 + NT;
   static_assert(B_COUNT * 8 <= 512, "barrier block");
   // TMEM columns (per tile: + TM_TILE * tile)
   static constexpr uint32_t TM_P = 0, TM_O = NT == 3 ? 128 : 192, TM_TILE = NT == 3 ? 160 : 256;
@@ -572,7 +573,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         const uint32_t lbo2 = n2 * 16u;
         const uint32_t qbytes = 12 * lbo2;  // one quarter's weight block: 12 K'-chunks of 8 halves
         const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
-        // NT = 3: O holds 32 columns, scaled layers take the shift rows (0..31 of the block) in this pass
+        // NT = 3: O holds 32 columns, scaled layers take the SCALE rows (32..63 of each quarter block, + 4 row
+        // groups of 128 bytes) in this pass: their epilogue is the long one, the shift pass runs under it
         const bool two_pass = NT == 3 && scaled;
         const uint32_t ih2 = (scaled && NT != 3) ? ih64 : ih32;
 #pragma unroll 1
@@ -587,7 +589,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           // quarter block in the chunk: FP16 [N2 x 96 K']: K' 0-31 w_hi (meets lo), 32-63 w_lo * 2^11 and
           // 64-95 w_hi * 2^11 (both meet the scaled hi block).  Chunk c = 2 q + half holds its operands in
           // place of its 16 H columns: 8 columns of packed lo pairs, 8 of packed scaled hi pairs.
-          const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? qbytes : 0);
+          const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? qbytes : 0) + (two_pass ? 512u : 0u);
           const uint64_t bd = make_desc(wbase, lbo2, 128);
           const uint32_t a0 = tb + TM_P + 32 * q;
           if (elect_one()) {
@@ -606,14 +608,15 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         }
         if constexpr (NT == 3) {
           if (scaled) {
-            // ---- second pass: the scale rows (32..63 of each quarter block, + 4 row groups of 128 bytes) over the
-            // same h operands, into the same 32 O columns once the epilogue has read the shifts out of them
+            // ---- second pass: the shift rows (0..31 of each quarter block) over the same h operands, into the
+            // same 32 O columns once the epilogue has read the scale pre-activations out of them
             mbar_wait(BAR(B_OCONS + t), sc_it & 1);
             tc_fence_after();
+            TR(32);
             if (elect_one()) {
 #pragma unroll 1
               for (int q = 0; q < 4; ++q) {
-                const uint64_t bd = make_desc(chunk_addr(g + 3 + q) + 512, lbo2, 128);
+                const uint64_t bd = make_desc(chunk_addr(g + 3 + q), lbo2, 128);
                 const uint32_t a0 = tb + TM_P + 32 * q;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -627,6 +630,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
               tc_commit(BAR(B_OFULL2 + t));
             }
             __syncwarp();
+            TR(33);
           }
         }
         g += layer_chunks(scaled);
@@ -818,8 +822,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     // touches (7..31) only contribute their squares, summed at the tile start.  At layer l feature f is GEMM2 output
     // column k = (f - 32 - l) mod 64, so O is read at a column offset of -l: entry i of the 32-column load is
     // feature 32 + i for i >= l (below that the feature is frozen and the word -- whatever lies left of O -- is
-    // discarded); features i < l sit at columns 32 - l + i.  Scaled layers: O receives the shifts, then (second
-    // MMA pass, after OCONS) the scale pre-activations.
+    // discarded); features i < l sit at columns 32 - l + i.  Scaled layers: O receives the scale
+    // pre-activations, then (second MMA pass, after OCONS, under the scale arithmetic) the shifts.
     const int wg = warp >> 2;              // 0..2 = tile
     const int tid = threadIdx.x & 127;     // TMEM lane == sample row within the tile
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
@@ -929,19 +933,15 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             }
           }
         }
-        // ---- E2, shifts
+        // ---- E2
         mbar_wait(BAR(B_OFULL + wg), par);
         tc_fence_after();
         TR(9);
-        {
+        if (!scaled) {
           uint32_t v0[U], v1[8];
           tmem_ld32(tm_o - l, v0);
           tmem_ld8(tm_o + U - l, v1);
           tmem_ld_wait();
-          if (scaled) {  // the MMA warp may overwrite O with the scale pass
-            tc_fence_before();
-            mbar_arrive(BAR(B_OCONS + wg));
-          }
 #pragma unroll
           for (int i = 0; i < U; ++i) {
             const float shift = __uint_as_float(v0[i]) + bl[i];
@@ -952,16 +952,17 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
             const float shift = __uint_as_float(v1[i]) + bl[U + i];
             x7[i] -= (i < l) ? shift : 0.f;
           }
-        }
-        if (scaled) {
-          // ---- E2, scales: y /= clip(softplus(a)), ldj -= sum log scale
-          mbar_wait(BAR(B_OFULL2 + wg), sc_it & 1);
-          tc_fence_after();
-          ++sc_it;
+        } else {
+          // Scaled layer: O holds the SCALE pre-activations first.  Once they are in registers the MMA warp may
+          // overwrite O with the shift pass (OCONS), which then runs under the softplus / reciprocal / log-det
+          // arithmetic below -- the long part of E2; the shifts are applied last: y = (y - t) * (1 / s).
           uint32_t v0[U], v1[8];
           tmem_ld32(tm_o - l, v0);
           tmem_ld8(tm_o + U - l, v1);
           tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(BAR(B_OCONS + wg));
+          // v0 / v1 become 1 / clip(softplus(a)) in place; ldj -= sum log scale
 #pragma unroll
           for (int k0 = 0; k0 < U; k0 += 8) {
             float prod = 1.f;  // 8 factors in [1e-3, 1e3] stay inside the float32 range
@@ -971,8 +972,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
               const float a = __uint_as_float(v0[i]) + bl[U + i];
               float sc = softplus_clip_fast(a);
               sc = (a != a) ? a : sc;  // keep NaN (fminf/fmaxf would drop it)
-              const float yn = yt[i] * rcp_approx(sc);
-              yt[i] = act ? yn : yt[i];
+              v0[i] = __float_as_uint(rcp_approx(sc));
               prod *= act ? sc : 1.f;
             }
             ldj -= 0.6931471805599453f * lg2_approx(prod);
@@ -985,11 +985,38 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
                 const float a = __uint_as_float(v1[i]) + bl[2 * U + i];
                 float sc = softplus_clip_fast(a);
                 sc = (a != a) ? a : sc;
-                x7[i] *= rcp_approx(sc);
+                v1[i] = __float_as_uint(rcp_approx(sc));
                 prod *= sc;
               }
             }
             ldj -= 0.6931471805599453f * lg2_approx(prod);
+          }
+          // shifts (second MMA pass), in two 16-column loads + the columns of the entered features
+          TR(11);
+          mbar_wait(BAR(B_OFULL2 + wg), sc_it & 1);
+          tc_fence_after();
+          TR(12);
+          ++sc_it;
+          uint32_t w0[16], w1[8];
+          tmem_ld16(tm_o - l, w0);
+          tmem_ld8(tm_o + U - l, w1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float yn = (yt[i] - (__uint_as_float(w0[i]) + bl[i])) * __uint_as_float(v0[i]);
+            yt[i] = (i >= NX || i >= l) ? yn : yt[i];
+          }
+          tmem_ld16(tm_o - l + 16, w0);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            const float xn = (x7[i] - (__uint_as_float(w1[i]) + bl[U + i])) * __uint_as_float(v1[i]);
+            x7[i] = (i < l) ? xn : x7[i];
+          }
+          tmem_ld_wait16(w0);
+#pragma unroll
+          for (int i = 16; i < U; ++i) {
+            const float yn = (yt[i] - (__uint_as_float(w0[i - 16]) + bl[i])) * __uint_as_float(v0[i]);
+            yt[i] = yn;  // features 48.. are transformed by every layer
           }
         }
         if (l + 1 < nl) {

@@ -19,10 +19,11 @@ import bench_workloads as wl  # noqa: E402
 from harmonic_b200 import _lib  # noqa: E402
 
 NAMES = {1: "tile start", 2: "A written (A1FULL arrive)", 3: "HFULL seen", 4: "E1 q0 done", 5: "E1 q1 done",
-         6: "E1 q2 done", 7: "E1 q3 done", 9: "OFULL seen", 10: "E2 done", 20: "mma: A1FULL seen",
+         6: "E1 q2 done", 7: "E1 q3 done", 9: "OFULL seen", 10: "E2 done", 11: "scale math done", 12: "OFULL2 seen", 20: "mma: A1FULL seen",
          21: "mma: corr issued", 22: "mma: A2 q0 seen", 23: "mma: A2 q1 seen", 24: "mma: A2 q2 seen",
          25: "mma: A2 q3 seen", 26: "mma: q0 issued", 27: "mma: q1 issued", 28: "mma: q2 issued",
-         29: "mma: q3 issued", 30: "mma: OFULL seen", 31: "mma: main issued"}
+         29: "mma: q3 issued", 30: "mma: OFULL seen", 31: "mma: main issued",
+         32: "mma: OCONS seen", 33: "mma: pass 2 issued"}
 
 
 def main():
