@@ -326,3 +326,37 @@ def test_realnvp_tcgen05_device_strided_and_f64(dtype):
     host = hm.Chains.from_arrays(view.cpu().numpy(), lnp.cpu().numpy(), start)
     ref = util.oracle_evidence(m, host)
     util.assert_evidence_close(ev, ref)
+
+
+# ------------------------------------------------------------------ tcgen05 path: the two-tile layout kept for A/B
+_TWO_TILE_SCRIPT = r"""
+import numpy as np
+import harmonic_b200 as hm
+from harmonic_b200 import _lib
+from tests import util
+for layers in ((2, 4), (8, 0), (1, 7)):
+    m = util.make_realnvp(64, layers[0], layers[1], seed=5, standardize=True, ws=0.5)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = np.random.default_rng(6).standard_normal((5000, 64)) * 1.2
+    util.check_predict(m, x, m.predict(x))
+m = util.make_realnvp(64, seed=9, standardize=True, ws=0.3)
+ch = util.gaussian_chains(64, 24, 900, seed=3, ragged=True)
+ev = hm.Evidence(ch.nchains, m)
+ev.add_chains(ch)
+util.assert_evidence_close(ev, util.oracle_evidence(m, ch))
+print("two-tile ok")
+"""
+
+
+def test_realnvp_tcgen05_two_tile_layout():
+    """HB_TC_TILES=2 (read once per process) selects the two-tile layout of realnvp_tc_kernel, kept for A/B
+    measurements against the default three-tile layout: it must stay parity-green too."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HB_TC_TILES="2")
+    out = subprocess.run([sys.executable, "-c", _TWO_TILE_SCRIPT], cwd=root, env=env, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and "two-tile ok" in out.stdout, out.stdout + out.stderr
