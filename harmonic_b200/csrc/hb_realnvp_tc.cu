@@ -67,8 +67,8 @@ constexpr int TILE = 128;
 constexpr int SLOT_BYTES = 16384;
 constexpr int MAX_TC_LAYERS = 8;  // one K = 8 correction step holds 7 new columns + the bias column
 constexpr int KA = 40;            // A operand columns: 32 raw + 7 new + 1 constant
-constexpr int A_HALF = KA / 4 * 2048;  // bytes of the hi (or lo) half of a tile's A operand
-constexpr int A_TILE = 2 * A_HALF;
+constexpr int A_HALF = 0;         // (offset of the FP16 block inside a tile's A operand: it is the whole operand)
+constexpr int A_TILE = KA / 4 * 2048;  // FP16 block, 10 chunks of 8 columns: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
 
 // Layout for NT tiles (= epilogue warpgroups) in flight per CTA.
 //   NT = 2: TMEM per tile P 128 | 64 unused | O 64; 8 weight slots; y[64] per thread with a register rotation
@@ -77,7 +77,7 @@ constexpr int A_TILE = 2 * A_HALF;
 //           epilogue keeps only the 32 transformed features + the 7 that can enter (owned by ORIGINAL index)
 template <int NT>
 struct L {
-  static constexpr int NSLOTS = NT == 3 ? 6 : 8;
+  static constexpr int NSLOTS = 8;
   static constexpr int THREADS = NT * 128 + 32 * (NT + 1);  // + producer warp + one MMA warp per tile
   // shared memory carve-up (bytes)
   static constexpr int SM_RING = 0;
@@ -205,6 +205,11 @@ __device__ __forceinline__ uint32_t pack_f16x2(float hi_elem, float lo_elem) {
 __device__ __forceinline__ uint16_t to_f16(float v) {
   uint16_t d;
   asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(d) : "f"(v));
+  return d;
+}
+__device__ __forceinline__ float from_f16(uint16_t h) {
+  float d;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(d) : "h"(h));
   return d;
 }
 #define HB_R32(v, o)                                                                                  \
@@ -383,13 +388,9 @@ __device__ __forceinline__ void load_row<double>(const double* __restrict__ x, l
   }
 }
 
-// The hi half of the FP16 correction operand is stored as a_hi * 2^-11 and meets w_lo * 2^11: both factors
-// then sit at the magnitude of a_lo / w_hi, well inside the normal half range (unscaled, w_lo of a typical
-// 0.03 weight is a subnormal half and costs ~1e-6 relative per product).
-constexpr float HI_SCALE = 4.8828125e-4f;
-// GEMM2 runs entirely as kind::f16: one FP16 MMA covers K = 16 at the same ~45-cycle cost as a TF32 MMA
+// Both GEMMs run entirely as kind::f16: one FP16 MMA covers K = 16 at the same ~45-cycle cost as a TF32 MMA
 // covering K = 8 (profiles/r1_mma_probe.txt), and an 11-bit significand is all the main term needs.
-// Compensated split of h:  hs = fp16(h * 2^-11) (round to nearest),  lo = h - 2^11 * float(hs)  (exact in
+// Compensated split of an activation h (GEMM1: a standardised input x):  hs = fp16(h * 2^-11) (round to nearest),  lo = h - 2^11 * float(hs)  (exact in
 // float32, whatever hs lost to rounding or to the half subnormal range), stored as fp16(lo).  Then
 //   h . w  ~=  hs . (w_hi * 2^11)  +  hs . (w_lo * 2^11)  +  lo . w_hi       (the lo . w_lo term, <= 2^-22, dropped)
 // with all products exact in the tensor core.  hs is a normal half for |h| in [0.125, 1.3e8]; below that lo
@@ -511,13 +512,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     // released when both warps have committed on it (WEMPTY expects two arrivals).
     const int t = warp - W_MMA;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
-    const uint32_t id128 = make_idesc(128);
     const uint32_t ih128 = make_idesc_f16(128), ih64 = make_idesc_f16(64), ih32 = make_idesc_f16(32);
-    const uint32_t a_x = sbase + SM_A1 + t * A_TILE;           // TF32 block: raw features, K-chunks 0..7
-    const uint32_t a_new = a_x + 8 * 2048;                      // TF32 block: new columns + constant one
-    const uint32_t a_h = a_x + A_HALF;                          // FP16 block: lo raw 0-3 | hi raw 4-7 | lo new 8 | hi new 9
-    const uint64_t adx_hi = make_desc(a_x, 2048, 128), adx_f16 = make_desc(a_h, 2048, 128);
-    const uint64_t adn_hi = make_desc(a_new, 2048, 128), adn_f16 = make_desc(a_h + 8 * 2048, 2048, 128);
+    const uint32_t a_h = sbase + SM_A1 + t * A_TILE;  // FP16 block: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
+    const uint64_t adx_f16 = make_desc(a_h, 2048, 128), adn_f16 = make_desc(a_h + 8 * 2048, 2048, 128);
     auto wwait = [&](uint32_t gidx) {
       mbar_wait(BAR(B_WFULL + (gidx % NSLOTS)), (gidx / NSLOTS) & 1);
     };
@@ -526,8 +523,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       if (elect_one()) tc_commit(BAR(B_WEMPTY + (gidx % NSLOTS)));
       __syncwarp();
     };
-    // main part of GEMM1: H = x(0..31) . W0main.  Chunk g+1 = FP16 correction operand [128 x 64 K'],
-    // chunk g = TF32 hi operand [128 x 32]; corrections first (small terms), then the main term.
+    // main part of GEMM1: H = x(0..31) . W0main, three FP16 products on the compensated split of x (as GEMM2).
+    // Chunk g+1 = FP16 [128 x 64 K']: w_hi (meets lo) | w_lo * 2^11 (meets hs); chunk g = FP16 [128 x 32 K']:
+    // w_hi * 2^11 (meets the same hs block); corrections first (small terms), then the main term.
     auto issue_main = [&](uint32_t g) {
       wwait(g);
       wwait(g + 1);
@@ -538,8 +536,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         for (int k = 0; k < 4; ++k)
           mma_ss_f16(tb + TM_P, adx_f16 + (uint64_t)(k * 256), wh + (uint64_t)(k * 256), ih128, k ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_ss(tb + TM_P, adx_hi + (uint64_t)(k * 256), wt + (uint64_t)(k * 256), id128, 1);
+        for (int k = 0; k < 2; ++k)
+          mma_ss_f16(tb + TM_P, adx_f16 + (uint64_t)((2 + k) * 256), wt + (uint64_t)(k * 256), ih128, 1);
       }
       __syncwarp();
     };
@@ -558,8 +556,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         {
           const uint64_t wc = make_desc(chunk_addr(g + 2), 2048, 128);
           if (elect_one()) {
-            mma_ss_f16(tb + TM_P, adn_f16, wc + (uint64_t)(4096 >> 4), ih128, 1);  // K' = 16: [lo new | hi new]
-            mma_ss(tb + TM_P, adn_hi, wc, id128, 1);                               // K = 8 TF32
+            // K' = 16 each over A = [lo new | hs new]: B = [w_hi ; w_lo * 2^11], then B = [0 ; w_hi * 2^11]
+            mma_ss_f16(tb + TM_P, adn_f16, wc + (uint64_t)(4096 >> 4), ih128, 1);
+            mma_ss_f16(tb + TM_P, adn_f16, wc, ih128, 1);
             tc_commit(BAR(B_HFULL + t));
             tc_commit(BAR(B_WEMPTY + (g % NSLOTS)));
             tc_commit(BAR(B_WEMPTY + ((g + 1) % NSLOTS)));
@@ -687,29 +686,22 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       // (GEMM1 of the previous tile has completed: its HFULL was waited.)
 #pragma unroll
       for (int c = 0; c < DH / 8; ++c) {
-        uint4 hi0, hi1, plo, phi;
-        uint32_t* p0 = &hi0.x;
-        uint32_t* p1 = &hi1.x;
+        uint4 plo, phi;
         uint32_t* ql = &plo.x;
         uint32_t* qh = &phi.x;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float va = y[8 * c + 2 * q], vb = y[8 * c + 2 * q + 1];
-          const uint32_t ha = __float_as_uint(va) & 0xffffe000u, hb = __float_as_uint(vb) & 0xffffe000u;
-          (q < 2 ? p0 : p1)[(2 * q) & 3] = ha;
-          (q < 2 ? p0 : p1)[(2 * q + 1) & 3] = hb;
-          ql[q] = pack_f16x2(vb - __uint_as_float(hb), va - __uint_as_float(ha));
-          qh[q] = pack_f16x2(__uint_as_float(hb) * HI_SCALE, __uint_as_float(ha) * HI_SCALE);
+          const uint32_t hs = pack_f16x2(vb * H2_SCALE, va * H2_SCALE);
+          const float2 bk = unpack_f16x2(hs);
+          ql[q] = pack_f16x2(fmaf(bk.y, -H2_INV, vb), fmaf(bk.x, -H2_INV, va));
+          qh[q] = hs;
         }
-        *reinterpret_cast<uint4*>(a1 + (2 * c) * 2048 + tid * 16) = hi0;
-        *reinterpret_cast<uint4*>(a1 + (2 * c + 1) * 2048 + tid * 16) = hi1;
         *reinterpret_cast<uint4*>(a1 + A_HALF + c * 2048 + tid * 16) = plo;
         *reinterpret_cast<uint4*>(a1 + A_HALF + (4 + c) * 2048 + tid * 16) = phi;
       }
       {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = z;
-        *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x3f800000u);
         *reinterpret_cast<uint4*>(a1 + A_HALF + 8 * 2048 + tid * 16) = z;
         *reinterpret_cast<uint4*>(a1 + A_HALF + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x10000000u);
       }
@@ -785,11 +777,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           // feature (logical 32) is frozen from here on: it is the new conditioning column l of the
           // following layers
           const float v = y[DH];
-          const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
-          const int col = DH + l;
-          *reinterpret_cast<uint32_t*>(a1 + (col >> 2) * 2048 + tid * 16 + (col & 3) * 4) = hb;
-          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 8 * 2048 + tid * 16 + l * 2) = to_f16(v - __uint_as_float(hb));
-          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 9 * 2048 + tid * 16 + l * 2) = to_f16(__uint_as_float(hb) * HI_SCALE);
+          const uint16_t hs16 = to_f16(v * H2_SCALE);
+          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 8 * 2048 + tid * 16 + l * 2) = to_f16(fmaf(from_f16(hs16), -H2_INV, v));
+          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 9 * 2048 + tid * 16 + l * 2) = hs16;
           // inverse of tfb.Permute([D-1, 0, .., D-2]): rotate left by one (flows.py:65-66)
           const float y0 = y[0];
 #pragma unroll
@@ -862,29 +852,22 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         // A operand, written once per tile (layout as in the NT = 2 branch)
 #pragma unroll
         for (int c = 0; c < DH / 8; ++c) {
-          uint4 hi0, hi1, plo, phi;
-          uint32_t* p0 = &hi0.x;
-          uint32_t* p1 = &hi1.x;
+          uint4 plo, phi;
           uint32_t* ql = &plo.x;
           uint32_t* qh = &phi.x;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float va = y[8 * c + 2 * q], vb = y[8 * c + 2 * q + 1];
-            const uint32_t ha = __float_as_uint(va) & 0xffffe000u, hb = __float_as_uint(vb) & 0xffffe000u;
-            (q < 2 ? p0 : p1)[(2 * q) & 3] = ha;
-            (q < 2 ? p0 : p1)[(2 * q + 1) & 3] = hb;
-            ql[q] = pack_f16x2(vb - __uint_as_float(hb), va - __uint_as_float(ha));
-            qh[q] = pack_f16x2(__uint_as_float(hb) * HI_SCALE, __uint_as_float(ha) * HI_SCALE);
+            const uint32_t hs = pack_f16x2(vb * H2_SCALE, va * H2_SCALE);
+            const float2 bk = unpack_f16x2(hs);
+            ql[q] = pack_f16x2(fmaf(bk.y, -H2_INV, vb), fmaf(bk.x, -H2_INV, va));
+            qh[q] = hs;
           }
-          *reinterpret_cast<uint4*>(a1 + (2 * c) * 2048 + tid * 16) = hi0;
-          *reinterpret_cast<uint4*>(a1 + (2 * c + 1) * 2048 + tid * 16) = hi1;
           *reinterpret_cast<uint4*>(a1 + A_HALF + c * 2048 + tid * 16) = plo;
           *reinterpret_cast<uint4*>(a1 + A_HALF + (4 + c) * 2048 + tid * 16) = phi;
         }
         {
           const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = z;
-          *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x3f800000u);
           *reinterpret_cast<uint4*>(a1 + A_HALF + 8 * 2048 + tid * 16) = z;
           *reinterpret_cast<uint4*>(a1 + A_HALF + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x10000000u);
         }
@@ -1024,11 +1007,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           float v = yt[0];
 #pragma unroll
           for (int i = 1; i < NX; ++i) v = (l == i) ? yt[i] : v;
-          const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
-          const int col = DH + l;
-          *reinterpret_cast<uint32_t*>(a1 + (col >> 2) * 2048 + tid * 16 + (col & 3) * 4) = hb;
-          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 8 * 2048 + tid * 16 + l * 2) = to_f16(v - __uint_as_float(hb));
-          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 9 * 2048 + tid * 16 + l * 2) = to_f16(__uint_as_float(hb) * HI_SCALE);
+          const uint16_t hs16 = to_f16(v * H2_SCALE);
+          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 8 * 2048 + tid * 16 + l * 2) = to_f16(fmaf(from_f16(hs16), -H2_INV, v));
+          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 9 * 2048 + tid * 16 + l * 2) = hs16;
         }
         TR(10);
       }
@@ -1088,11 +1069,8 @@ static inline void split_tf32(float v, float* hi, float* lo) {
   *lo = v - *hi;
 }
 
-// element (n, k) of a K-major [N x K] block in the canonical no-swizzle layout, in floats
-static inline size_t kmajor_off(int N, int n, int k) {
-  return (size_t)(n / 8) * 32 + (size_t)(n % 8) * 4 + (size_t)(k / 4) * (N * 4) + (k % 4);
-}
-// same for a 16-bit operand (8 elements per 16-byte chunk), in halves
+// element (n, k) of a K-major [N x K] 16-bit operand in the canonical no-swizzle layout (8 elements per 16-byte
+// chunk), in halves
 static inline size_t kmajor_off16(int N, int n, int k) {
   return (size_t)(n / 8) * 64 + (size_t)(n % 8) * 8 + (size_t)(k / 8) * (N * 8) + (k % 8);
 }
@@ -1125,14 +1103,14 @@ static inline uint16_t f32_to_f16(float f) {
   return (uint16_t)(sign | (he << 10) | (q & 0x3ffu));
 }
 
-// one weight w into the TF32 main operand (hi) and the FP16 correction operand: row kh holds fp16(hi)
-// (meets a_lo), row kl holds fp16(lo) (meets a_hi)
-static inline void put_weight(float w, float* t32, size_t off32, uint16_t* h16, size_t off_hi, size_t off_lo) {
+// one weight w = hi + lo (hi: 11 significant bits) into the three FP16 operands: m16[off_main] = fp16(hi * 2^11)
+// (main term, meets hs), h16[off_hi] = fp16(hi) (meets lo), h16[off_lo] = fp16(lo * 2^11) (meets hs)
+static inline void put_weight(float w, uint16_t* m16, size_t off_main, uint16_t* h16, size_t off_hi, size_t off_lo) {
   float hi, lo;
   split_tf32(w, &hi, &lo);
-  t32[off32] = hi;
+  m16[off_main] = f32_to_f16(hi * 2048.0f);
   h16[off_hi] = f32_to_f16(hi);
-  h16[off_lo] = f32_to_f16(lo * 2048.0f);  // 1 / HI_SCALE
+  h16[off_lo] = f32_to_f16(lo * 2048.0f);
 }
 
 int realnvp_tc_prepare(Flow* f) {
@@ -1142,12 +1120,13 @@ int realnvp_tc_prepare(Flow* f) {
   const int nl = f->nlayers;
   if (nl > tc::MAX_TC_LAYERS) return HB_OK;
   const int d = f->d, u = f->u;
-  // GEMM2 weights are stored * 2^11 as halves: |w| must stay below 65504 / 2048 (else the CUDA-core path runs)
+  // weights (and b0, which rides in W0') are stored * 2^11 as halves: |w| must stay below 65504 / 2048 (else the
+  // CUDA-core path runs)
   for (int l = 0; l < nl; ++l) {
-    const float* Wt = f->host_weights.data() + f->layer_off[l] + (size_t)d * 128 + 128;
-    const size_t n2 = (size_t)128 * u * ((l < ds.n_scaled) ? 2 : 1) + u;  // Wt, bt, (Ws): bt is harmless to include
+    const float* W0 = f->host_weights.data() + f->layer_off[l];
+    const size_t n2 = (size_t)d * 128 + 128 + (size_t)128 * u * ((l < ds.n_scaled) ? 2 : 1) + u;  // W0, b0, Wt, bt, (Ws)
     for (size_t i = 0; i < n2; ++i)
-      if (!(fabsf(Wt[i]) < 16.0f)) return HB_OK;
+      if (!(fabsf(W0[i]) < 16.0f)) return HB_OK;
   }
   const size_t CF = tc::SLOT_BYTES / 4;  // floats per chunk
   size_t nchunks = 0;
@@ -1165,27 +1144,29 @@ int realnvp_tc_prepare(Flow* f) {
     const float* Ws = bt + u;
     const float* bs = Ws + (size_t)128 * u;
     // GEMM1 main: A column i (original feature i < 32) meets W0 row i - l (zero for i < l).
-    // chunk 0: TF32 hi [128 x 32]; chunk 1: FP16 [128 x 64 K']: K' < 32 fp16(hi), K' >= 32 fp16(lo)
+    // chunk 0: FP16 [128 x 32 K'] fp16(hi * 2^11); chunk 1: FP16 [128 x 64 K']: K' < 32 fp16(hi), K' >= 32
+    // fp16(lo * 2^11)
     {
-      float* c0 = img.data() + ch * CF;
+      uint16_t* c0 = reinterpret_cast<uint16_t*>(img.data() + ch * CF);
       uint16_t* c1 = reinterpret_cast<uint16_t*>(img.data() + (ch + 1) * CF);
       for (int i = 0; i < 32; ++i)
         for (int n = 0; n < 128; ++n) {
           const float v = (i >= l) ? W0[(size_t)(i - l) * 128 + n] : 0.f;
-          put_weight(v, c0, kmajor_off(128, n, i), c1, kmajor_off16(128, n, i), kmajor_off16(128, n, 32 + i));
+          put_weight(v, c0, kmajor_off16(128, n, i), c1, kmajor_off16(128, n, i), kmajor_off16(128, n, 32 + i));
         }
     }
     // GEMM1 correction (chunk 2): k = 0..6 <-> frozen feature 32 + j meets W0 row 32 - l + j (j < l),
-    // k = 7 <-> constant-one column carrying the bias b0.  TF32 hi [128 x 8] 4 KB | FP16 [128 x 16 K'] 4 KB
+    // k = 7 <-> constant-one column carrying the bias b0.  FP16 [128 x 16 K'] 4 KB: K' < 8 zero (meets lo new),
+    // K' >= 8 fp16(hi * 2^11) (meets hs new) | FP16 [128 x 16 K'] 4 KB: fp16(hi) | fp16(lo * 2^11)
     {
-      float* c = img.data() + (ch + 2) * CF;
-      uint16_t* ch16 = reinterpret_cast<uint16_t*>(c + 1024);
+      uint16_t* c = reinterpret_cast<uint16_t*>(img.data() + (ch + 2) * CF);
+      uint16_t* ch16 = c + 2048;
       for (int k = 0; k < 8; ++k)
         for (int n = 0; n < 128; ++n) {
           float v = 0.f;
           if (k == 7) v = b0[n];
           else if (k < l) v = W0[(size_t)(32 - l + k) * 128 + n];
-          put_weight(v, c, kmajor_off(128, n, k), ch16, kmajor_off16(128, n, k), kmajor_off16(128, n, 8 + k));
+          put_weight(v, c, kmajor_off16(128, n, 8 + k), ch16, kmajor_off16(128, n, k), kmajor_off16(128, n, 8 + k));
         }
     }
     // GEMM2: B[n][k] = [Wt | Ws][k][n]; one K = 32 quarter = FP16 block [N2 x 96 K']: K' < 32 fp16(w_hi) (meets
