@@ -376,18 +376,21 @@ def main():
         peak = float(peaks["bf16_tflops"]) / 2.0
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None,
-                # ncu --set full (profiles/r1_prof_tc_r1k_raw_summary.csv): 262.3 B of DRAM traffic per sample
-                # (read 260.4 + write 1.9; algorithmic 260 B): the kernel is not memory bound
-                "traffic": 262.3 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
+                # ncu --set full (profiles/r1_prof_tc_r1l_raw_summary.csv): 262.5 B of DRAM traffic per sample
+                # (read 260.4 + write 2.1; algorithmic 260 B): the kernel is not memory bound
+                "traffic": 262.5 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
                 "kernel": "realnvp_tc_kernel", "kernel_ms": kms,
-                "peak_source": "TF32 dense = bf16 burst / 2, of %s" % peak_kind,
-                # issued: 0.54x as kind::tf32 (GEMM1 main term, K 32 -> 40) + 2.79x as kind::f16 (GEMM1 corrections,
-                # all of GEMM2); a tcgen05.mma costs max(~45, N/2) cycles whatever its kind (profiles/r1_mma_probe.txt).
-                # Three tiles in flight leave 32 accumulator columns per tile, so the 2 scaled layers run GEMM2 in two
-                # N = 32 passes: 10 x 64.4 + (2 x 48 + 4 x 24)/6 x 45 = 2084 tensor-pipe cycles per 128-sample tile and
-                # layer => pipe bound 35.7 ms for 1e8 samples at 1.85 GHz, i.e. frac <= 0.39 for this instruction mix
-                "issued_mma_flop_factor": 3.32, "issued_tf32_time_factor": 1.93,
-                "mma_instructions_per_tile_layer": 42, "tensor_pipe_cycles_per_tile_layer": 2084,
+                "peak_source": "TF32 dense = bf16 burst / 2, of %s (the roofline BASELINE.json names; the kernel issues "
+                               "kind::f16 MMAs, against the measured 16-bit peak the fraction is half of frac)" % peak_kind,
+                "frac_of_16bit_peak": (ach / (2.0 * peak)) if ach else None,
+                # issued: 3.43x the algorithmic FLOP, all as kind::f16 (three FP16 products on compensated splits of
+                # activations and weights, GEMM1 K 32 -> 40); a tcgen05.mma costs max(~45, N/2) cycles whatever its kind
+                # (profiles/r1_mma_probe.txt).  Three tiles in flight leave 32 accumulator columns per tile, so the 2
+                # scaled layers run GEMM2 in two N = 32 passes: 8 x 64.4 + (2 x 48 + 4 x 24)/6 x 45 = 1955 tensor-pipe
+                # cycles per 128-sample tile and layer => pipe bound 33.5 ms for 1e8 samples at 1.85 GHz, i.e.
+                # frac <= 0.42 for this instruction mix
+                "issued_mma_flop_factor": 3.43, "issued_tf32_time_factor": 1.71,
+                "mma_instructions_per_tile_layer": 40, "tensor_pipe_cycles_per_tile_layer": 1955,
                 "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
     else:
         # small-ndim flows run on the FP32 CUDA cores (tensor tiles would be >= 75 % padding):
@@ -423,7 +426,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32/f16 split (f32-equivalent products, f32 accumulate)" if (name == "cfg4" and args.path != "simt") else "f32",
+        "vs_baseline": None, "dtype": "f16 3-product split on tcgen05 (f32-equivalent products, f32 accumulate)" if (name == "cfg4" and args.path != "simt") else "f32",
         "data": "synthetic", "config": workload_config(name, world, nchains, per_chain),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "result": {"ln_evidence_inv": float(ev.ln_evidence_inv), "ln_evidence_inv_var": float(ev.ln_evidence_inv_var),
