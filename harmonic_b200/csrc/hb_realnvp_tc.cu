@@ -9,9 +9,9 @@
 //   NT epilogue warpgroups : each owns one tile at a time, one sample per thread (TMEM lane = sample).
 //                     NT = 3 (128 registers per thread): the 32 initially transformed features + the 7 that
 //                     can enter, owned by ORIGINAL index; NT = 2: y[64] with a register rotation per layer
-//   producer warp   : streams the pre-split weight image (TF32 hi + FP16 correction blocks, UMMA canonical
-//                     no-swizzle K-major layout, built once on the host) from L2 into a ring of 16 KiB
-//                     chunks (6 slots for NT = 3, 8 for NT = 2) with cp.async.bulk + mbarrier
+//   producer warp   : streams the pre-split weight image (FP16 blocks, UMMA canonical no-swizzle K-major
+//                     layout, built once on the host) from L2 into an 8-slot ring of 16 KiB chunks with
+//                     cp.async.bulk + mbarrier
 //   NT MMA warps    : tcgen05.mma issuers, one per tile (the first also allocates TMEM); warp-uniform
 //                     straight-line program with blocking mbarrier waits, one elected lane issues
 //
@@ -20,14 +20,13 @@
 //   E1     h = leaky_relu(H), compensated FP16 split, in place   eight 16-column chunks, TMEM loads prefetched
 //   GEMM2  O[128xN2] += h[:, quarter] . [Wt|Ws][quarter, :]      A from TMEM, 6 FP16 MMAs per K = 32 quarter
 //   E2     shift / softplus-clip scale epilogue on y1, log-det
-// Split-precision contractions with FP32 accumulation in TMEM, float32-equivalent products (~2^-22).
-// GEMM1: a.w ~= a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo), hi = top 19 bits (a TF32 value), lo = exact remainder; the
-// main term runs as kind::tf32 (any input magnitude), the two correction terms as ONE kind::f16 contraction over
-// K' = [a_lo | a_hi * 2^-11] . [w_hi ; w_lo * 2^11].
-// GEMM2: entirely kind::f16 (see the comment at H2_SCALE): hs = fp16(h * 2^-11), lo = h - 2^11 hs, and
-// h.w ~= hs.(w_hi 2^11) + hs.(w_lo 2^11) + lo.w_hi -- the SAME hs block feeds two MMAs.  A tcgen05.mma costs
-// max(~45, N/2) cycles whatever its kind (profiles/r1_mma_probe.txt), so for the N = 64 / 32 steps of GEMM2 the
-// instruction count is the resource: 6 FP16 MMAs (K = 16 each) per quarter instead of 4 TF32 + 4 FP16.
+// Split-precision contractions with FP32 accumulation in TMEM, float32-equivalent products (~2^-22), every MMA
+// kind::f16 (see the comment at H2_SCALE).  An activation a (GEMM1: a standardised input, GEMM2: a hidden unit) is
+// split with compensation, hs = fp16(a * 2^-11), lo = fp16(a - 2^11 hs); a weight as w_hi (11 significant bits) +
+// w_lo; then  a.w ~= hs.(w_hi 2^11) + hs.(w_lo 2^11) + lo.w_hi  -- the SAME hs block feeds two MMAs.  A tcgen05.mma
+// costs max(~45, N/2) cycles whatever its kind (profiles/r1_mma_probe.txt), so the instruction count is the
+// resource and an FP16 MMA covers K = 16 where a TF32 MMA covers K = 8: GEMM1 8 MMAs per layer (2 main + 4
+// correction over x(0..31), 2 over the new columns + bias), GEMM2 6 per K = 32 quarter.
 // What remains against a float32 FMA chain is the tensor cores' truncating accumulator
 // (profiles/r1_tensor_accum_rounding.txt), see DESIGN.md 4.1.
 //
@@ -71,9 +70,9 @@ constexpr int A_HALF = 0;         // (offset of the FP16 block inside a tile's A
 constexpr int A_TILE = KA / 4 * 2048;  // FP16 block, 10 chunks of 8 columns: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
 
 // Layout for NT tiles (= epilogue warpgroups) in flight per CTA.
-//   NT = 2: TMEM per tile P 128 | 64 unused | O 64; 8 weight slots; y[64] per thread with a register rotation
+//   NT = 2: TMEM per tile P 128 | 64 unused | O 64; y[64] per thread with a register rotation
 //   NT = 3: TMEM per tile P 128 | O 32 (480 of 512 columns): scaled layers run GEMM2 in TWO N = 32 passes over the
-//           same h operands (shift, then scale, see the kernel); 6 weight slots; 128 registers per thread, so the
+//           same h operands (scale, then shift, see the kernel); 128 registers per thread, so the
 //           epilogue keeps only the 32 transformed features + the 7 that can enter (owned by ORIGINAL index)
 template <int NT>
 struct L {
@@ -81,7 +80,7 @@ struct L {
   static constexpr int THREADS = NT * 128 + 32 * (NT + 1);  // + producer warp + one MMA warp per tile
   // shared memory carve-up (bytes)
   static constexpr int SM_RING = 0;
-  static constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;       // per tile: hi | lo
+  static constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;       // per tile: the FP16 A operand (A_TILE)
   static constexpr int SM_BIAS = SM_A1 + NT * A_TILE;               // b2: MAX_TC_LAYERS * 64 floats
   static constexpr int SM_PRE = SM_BIAS + MAX_TC_LAYERS * 64 * 4;   // standardisation: inv_amp[D], -offset*inv_amp[D]
   static constexpr int SM_BAR = SM_PRE + 2 * D * 4;                 // mbarriers
