@@ -495,12 +495,18 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       uint32_t g = 0;
       for (int b = 0; b < P.nbatches; ++b) {
         const uint8_t* src = P.image;
-        for (int c = 0; c < P.chunks_per_batch; ++c, ++g) {
-          const uint32_t slot = g % NSLOTS, use = g / NSLOTS;
-          mbar_wait(BAR(B_WEMPTY + slot), (use & 1) ^ 1);
-          mbar_expect_tx(BAR(B_WFULL + slot), SLOT_BYTES);
-          bulk_g2s(sbase + SM_RING + slot * SLOT_BYTES, src, SLOT_BYTES, BAR(B_WFULL + slot));
-          src += SLOT_BYTES;
+        for (int l = 0; l < nl; ++l) {
+          const int nc = layer_chunks(l < P.nscaled);
+          for (int j = 0; j < nc; ++j, ++g) {
+            // only the occupied prefix of a chunk travels: GEMM1 main hs block 8 KiB, [lo | hs] block 16 KiB, the
+            // two new-column blocks 8 KiB, a GEMM2 chunk (one N2 = 64 quarter or two N2 = 32 quarters) 12 KiB
+            const uint32_t bytes = j == 1 ? 16384u : (j < 3 ? 8192u : 12288u);
+            const uint32_t slot = g % NSLOTS, use = g / NSLOTS;
+            mbar_wait(BAR(B_WEMPTY + slot), (use & 1) ^ 1);
+            mbar_expect_tx(BAR(B_WFULL + slot), bytes);
+            bulk_g2s(sbase + SM_RING + slot * SLOT_BYTES, src, bytes, BAR(B_WFULL + slot));
+            src += SLOT_BYTES;
+          }
         }
       }
     }
