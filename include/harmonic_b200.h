@@ -47,7 +47,8 @@ enum { HB_F32 = 0, HB_F64 = 1 };
 enum { HB_MEM_HOST = 0, HB_MEM_DEVICE = 1 };
 /* harmonic.evidence.Shifting (harmonic/evidence.py:11-20) */
 enum { HB_MEAN_SHIFT = 1, HB_MAX_SHIFT = 2, HB_MIN_SHIFT = 3, HB_ABS_MAX_SHIFT = 4 };
-/* kernel selection for RealNVP: AUTO picks tcgen05 when the shape is supported */
+/* kernel selection for RealNVP: AUTO picks tcgen05 when the flow is supported there (ndim 64, hidden 128, <= 8
+ * coupling layers, every conditioner weight and bias |w| < 16: the tensor path stores them * 2^11 as halves) */
 enum { HB_PATH_AUTO = 0, HB_PATH_SIMT = 1, HB_PATH_TCGEN05 = 2, HB_PATH_SIMT_GENERIC = 3 /* no small-ndim register path */ };
 /* flags for hb_accumulate_* */
 enum { HB_ACC_NEW_CALL = 1 /* first launch of an add_chains call: reset the per-call scalars */ };
