@@ -17,6 +17,7 @@ HB_F32, HB_F64 = 0, 1
 HB_MEM_HOST, HB_MEM_DEVICE = 0, 1
 HB_PATH_AUTO, HB_PATH_SIMT, HB_PATH_TCGEN05, HB_PATH_SIMT_GENERIC = 0, 1, 2, 3
 HB_ACC_NEW_CALL = 1
+HB_MERGE_OVERWRITE = 1
 HB_MAX_HIDDEN = 8
 HB_ERR_INVALID, HB_ERR_CUDA, HB_ERR_UNSUPPORTED, HB_ERR_NO_DEVICE = -1, -2, -3, -4
 
@@ -34,7 +35,7 @@ class Result(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "ln_evidence_inv", "ln_evidence_inv_var", "ln_evidence_inv_var_var", "ln_kurtosis", "n_eff",
         "shift_value", "lnargmax", "lnargmin", "lnprobmax", "lnprobmin", "lnpredictmax",
-        "lnpredictmin", "nsamples_total")] + [("reserved", C.c_double * 3)]
+        "lnpredictmin", "nsamples_total", "mean_nsamples_eff", "guard_trips", "reserved")]
 
 
 # name -> (restype, argtypes); mirrors include/harmonic_b200.h one to one
@@ -53,18 +54,21 @@ SIGNATURES = {
                                  C.c_int, C.c_void_p]),
     "hb_accum_create": (C.c_int, [C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     "hb_accum_destroy": (C.c_int, [C.c_void_p]),
-    "hb_accum_reset": (C.c_int, [C.c_void_p]),
+    "hb_accum_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hb_pool_trim": (C.c_int, []),
     "hb_accumulate_flow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int64,
                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_int, C.c_void_p]),
     "hb_accumulate_precomputed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                             C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
-    "hb_accum_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "hb_accum_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_accum_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_accum_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_accum_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "hb_accum_merge_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "hb_accum_packed_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "hb_accum_merge_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "hb_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(Result), C.c_void_p, C.c_void_p,
-                              C.c_void_p, C.c_void_p]),
+                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_finalize_arrays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_finalize_realspace": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
                                         C.POINTER(Result), C.c_void_p]),
     "hb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -76,7 +80,9 @@ SIGNATURES = {
     "hb_stream_sync": (C.c_int, [C.c_void_p]),
     "hb_launch_count": (C.c_int64, []),
     "hb_set_kernel_timing": (C.c_int, [C.c_int]),
-    "hb_last_kernel_ms": (C.c_double, []),
+    "hb_last_kernel_ms": (C.c_double, [C.c_int]),
+    "hb_bind_host_to_device_node": (C.c_int, [C.c_int]),
+    "hb_host_copy_gbs": (C.c_double, [C.c_size_t, C.c_int]),
 }
 
 _lib = None

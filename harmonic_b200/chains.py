@@ -24,6 +24,15 @@ class Chains:
         self.nsamples = 0
         self.samples = np.empty((0, self.ndim))
         self.ln_posterior = np.empty((0))
+        self._start_np = None  # int64 image of start_indices (start_array)
+
+    def start_array(self):
+        """``start_indices`` as a contiguous int64 array (what the C ABI takes), cached while the list keeps
+        its length (every method of this class that edits the list drops the cache)."""
+        a = self._start_np
+        if a is None or a.shape[0] != len(self.start_indices):
+            a = self._start_np = np.ascontiguousarray(self.start_indices, dtype=np.int64)
+        return a
 
     # ---------------------------------------------------------------- zero-copy constructor
     @classmethod
@@ -32,14 +41,16 @@ class Chains:
         (numpy float32/float64 or CUDA tensors).  No copy, no dtype change."""
         ndim = int(samples.shape[1])
         ch = cls(ndim)
-        start = [int(s) for s in start_indices]
-        if start[0] != 0 or any(b < a for a, b in zip(start[:-1], start[1:])):
+        sa = np.array(start_indices, dtype=np.int64).reshape(-1)  # private copy
+        if sa.shape[0] < 1 or sa[0] != 0 or np.any(np.diff(sa) < 0):
             raise ValueError("start_indices must start at 0 and be non-decreasing")
+        start = sa.tolist()
         if start[-1] != int(samples.shape[0]) or int(ln_posterior.shape[0]) != int(samples.shape[0]):
             raise ValueError("Length of sample and ln_posterior arrays do not match")
         ch.samples = samples
         ch.ln_posterior = ln_posterior
         ch.start_indices = start
+        ch._start_np = sa
         ch.nchains = len(start) - 1
         ch.nsamples = start[-1]
         return ch
@@ -61,6 +72,7 @@ class Chains:
         self.nsamples += nsamples_in
         self.start_indices.append(self.nsamples)
         self.nchains += 1
+        self._start_np = None
 
     def _add_many(self, samples, ln_posterior, bounds):
         """Append several chains with ONE concatenation (the reference re-concatenates per chain)."""
@@ -73,6 +85,7 @@ class Chains:
             self.start_indices.append(int(base + b))
         self.nsamples = self.start_indices[-1]
         self.nchains += len(bounds) - 1
+        self._start_np = None
 
     # ---------------------------------------------------------------- harmonic/chains.py:73-130
     def add_chains_2d(self, samples, ln_posterior, nchains_in: int):
@@ -151,6 +164,7 @@ class Chains:
         self.ln_posterior = self.ln_posterior[keep]
         self.start_indices = [0] + [int(v) for v in np.cumsum(per - nburn)]
         self.nsamples = self.start_indices[-1]
+        self._start_np = None
 
     # ---------------------------------------------------------------- harmonic/chains.py:419-482
     def split_into_blocks(self, nblocks: int = 100):
@@ -175,3 +189,4 @@ class Chains:
             new_start.append(int(b))
         self.start_indices = new_start
         self.nchains = nblocks
+        self._start_np = None

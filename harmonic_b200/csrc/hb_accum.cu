@@ -23,36 +23,36 @@ constexpr int ACC_THREADS = 256;
 constexpr int ACC_R = 8;
 constexpr int ACC_TILE = ACC_THREADS * ACC_R;
 
-template <typename T>
-__device__ __forceinline__ void load8(const T* __restrict__ p, long long r, float (&v)[8]);
-
-// rows r .. r+3 and r + 4*ACC_THREADS .. +3: each 128-bit load is fully coalesced across the warp
-template <>
-__device__ __forceinline__ void load8<float>(const float* __restrict__ p, long long r, float (&v)[8]) {
+// rows r .. r+3 and r + 4*ACC_THREADS .. +3 in the element type of the buffer: each 128-bit load is fully
+// coalesced across the warp
+__device__ __forceinline__ void load8(const float* __restrict__ p, long long r, float (&v)[8]) {
   const float4* q = reinterpret_cast<const float4*>(p + r);
   float4 a = __ldcs(q), b = __ldcs(q + 256);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-template <>
-__device__ __forceinline__ void load8<double>(const double* __restrict__ p, long long r, float (&v)[8]) {
+__device__ __forceinline__ void load8(const double* __restrict__ p, long long r, double (&v)[8]) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const double2* q = reinterpret_cast<const double2*>(p + r + (long long)g * 4 * 256);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       double2 a = __ldcs(q + k);
-      v[4 * g + 2 * k] = (float)a.x;
-      v[4 * g + 2 * k + 1] = (float)a.y;
+      v[4 * g + 2 * k] = a.x;
+      v[4 * g + 2 * k + 1] = a.y;
     }
   }
 }
 
+// lnarg = lnpred - ln_posterior.  With a float64 operand the difference is formed in double and rounded to
+// float32 once (|ln_posterior| ~ 1e4 would otherwise cost ~1e-3 of cancellation error per lnarg): what numpy
+// does in the reference's per-sample branch (harmonic/evidence.py:285-303).
 template <typename PT, typename LT, bool VEC>
 __global__ void __launch_bounds__(ACC_THREADS, 6)
 accumulate_precomputed_kernel(const PT* __restrict__ lnpred, const LT* __restrict__ lnpost,
                               FoldParams p) {
   __shared__ double scratch[3 * (ACC_THREADS / 32)];
+  constexpr bool WIDE = sizeof(PT) == 8 || sizeof(LT) == 8;
   const long long row_lo = (long long)blockIdx.x * p.rows_per_flusher;
   long long row_hi = row_lo + p.rows_per_flusher;
   if (row_hi > p.nrows) row_hi = p.nrows;
@@ -60,21 +60,29 @@ accumulate_precomputed_kernel(const PT* __restrict__ lnpred, const LT* __restric
   Fold<ACC_THREADS> fold(p, blockIdx.x, threadIdx.x, scratch, had_rows ? row_lo : 0);
   for (long long t0 = row_lo; t0 < row_hi; t0 += ACC_TILE) {
     long long t1 = t0 + ACC_TILE;
-    float a[ACC_R], b[ACC_R];
+    PT pa[ACC_R];
+    LT pb[ACC_R];
     const long long r0 = t0 + (long long)threadIdx.x * 4;
     if (VEC && t1 <= row_hi) {
-      load8<PT>(lnpred, r0, a);
-      load8<LT>(lnpost, r0, b);
+      load8(lnpred, r0, pa);
+      load8(lnpost, r0, pb);
     } else {
       if (t1 > row_hi) t1 = row_hi;
 #pragma unroll
       for (int q = 0; q < ACC_R; ++q) {
         const long long r = r0 + (long long)(q / 4) * 4 * ACC_THREADS + (q % 4);
-        a[q] = (r < t1) ? (float)lnpred[r] : 0.f;
-        b[q] = (r < t1) ? (float)lnpost[r] : 0.f;
+        pa[q] = (r < t1) ? lnpred[r] : (PT)0;
+        pb[q] = (r < t1) ? lnpost[r] : (LT)0;
       }
     }
-    fold.tile<ACC_R, 4>(t0, t1, a, b);
+    float a[ACC_R], b[ACC_R], d[ACC_R];
+#pragma unroll
+    for (int q = 0; q < ACC_R; ++q) {
+      a[q] = (float)pa[q];
+      b[q] = (float)pb[q];
+      if (WIDE) d[q] = (float)((double)pa[q] - (double)pb[q]);
+    }
+    fold.tile<ACC_R, 4>(t0, t1, a, b, WIDE ? d : nullptr);
   }
   fold.finish(had_rows);
 }
@@ -95,8 +103,9 @@ __device__ __forceinline__ void merge_pair(double& m0, double& s0, double m1, do
   m0 = M;
 }
 
-__global__ void merge_kernel(ChainState* __restrict__ state, double* __restrict__ globals,
-                             FoldParams p, long long chain_lo, long long nflushers) {
+__global__ void __launch_bounds__(256)
+merge_kernel(ChainState* __restrict__ state, double* __restrict__ globals, FoldParams p, long long chain_lo,
+             long long nflushers, int overwrite_globals) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < p.nch) {
     const long long a = p.start[c], b = p.start[c + 1];
@@ -114,38 +123,75 @@ __global__ void merge_kernel(ChainState* __restrict__ state, double* __restrict_
       state[chain_lo + c] = st;
     }
   }
-  // per-call scalars: warp k of block 0 reduces column k of gpart (lane-strided, then a shuffle
-  // tree: a fixed order, so the result is reproducible)
-  if (blockIdx.x == 0 && (threadIdx.x >> 5) < G_N) {
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double acc = (k < 2) ? 0.0 : ((k & 1) ? CUDART_INF : -CUDART_INF);
-    for (long long f = lane; f < nflushers; f += 32) {
-      const double o = p.gpart[f * G_N + k];
-      if (k < 2) acc += o;
-      else if (k & 1) acc = fmin(acc, o);
-      else acc = fmax(acc, o);
+  // per-call scalars: block 0 reduces the [nflushers][G_N] partials.  Thread t takes rows t, t + 256, ...
+  // (independent 64-byte loads), then a shuffle tree and one pass over the 8 warps: a fixed order, so the
+  // result is reproducible.
+  if (blockIdx.x == 0) {
+    __shared__ double sh[8][G_N];
+    double acc[G_N];
+#pragma unroll
+    for (int k = 0; k < G_N; ++k) acc[k] = (k < 2) ? 0.0 : ((k & 1) ? CUDART_INF : -CUDART_INF);
+    for (long long f = threadIdx.x; f < nflushers; f += 256) {
+      const double2* row = reinterpret_cast<const double2*>(p.gpart + f * G_N);
+#pragma unroll
+      for (int k = 0; k < G_N; k += 2) {
+        const double2 o = row[k >> 1];
+        if (k < 2) {
+          acc[k] += o.x;
+          acc[k + 1] += o.y;
+        } else {
+          acc[k] = fmax(acc[k], o.x);          // even k = maxima
+          acc[k + 1] = fmin(acc[k + 1], o.y);  // odd k = minima
+        }
+      }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const double v = __shfl_xor_sync(0xffffffffu, acc, o);
-      if (k < 2) acc += v;
-      else if (k & 1) acc = fmin(acc, v);
-      else acc = fmax(acc, v);
+    for (int k = 0; k < G_N; ++k) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const double v = __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (k < 2) acc[k] += v;
+        else if (k & 1) acc[k] = fmin(acc[k], v);
+        else acc[k] = fmax(acc[k], v);
+      }
     }
-    if (lane == 0) {
-      const double g = globals[k];
-      globals[k] = (k < 2) ? g + acc : ((k & 1) ? fmin(g, acc) : fmax(g, acc));
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < G_N; ++k) sh[threadIdx.x >> 5][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < G_N) {
+      const int k = threadIdx.x;
+      double r = sh[0][k];
+      for (int w = 1; w < 8; ++w) {
+        const double o = sh[w][k];
+        if (k < 2) r += o;
+        else if (k & 1) r = fmin(r, o);
+        else r = fmax(r, o);
+      }
+      if (!overwrite_globals) {
+        const double g = globals[k];
+        r = (k < 2) ? g + r : ((k & 1) ? fmin(g, r) : fmax(g, r));
+      }
+      globals[k] = r;
     }
   }
 }
 
-// fold nranks packed blocks ([4n partials | 8 globals], block r at packed + r*stride) in rank order
+// fold nranks packed blocks ([4n partials | 8 globals], block r at packed + r*stride) in rank order;
+// overwrite != 0: the result REPLACES the state (the all-gather target needs no separate reset)
 __global__ void merge_packed_kernel(ChainState* __restrict__ state, double* __restrict__ globals,
                                     const double* __restrict__ packed, long long stride, int nranks,
-                                    long long n) {
+                                    long long n, int overwrite) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c < n) {
-    ChainState st = state[c];
+    ChainState st;
+    if (overwrite) {
+      st.m = -CUDART_INF;
+      st.s = st.n = st.nnan = 0.0;
+    } else {
+      st = state[c];
+    }
     for (int r = 0; r < nranks; ++r) {
       const double* part = packed + (long long)r * stride;
       merge_pair(st.m, st.s, part[4 * c + 0], part[4 * c + 1]);
@@ -156,7 +202,7 @@ __global__ void merge_packed_kernel(ChainState* __restrict__ state, double* __re
   }
   if (blockIdx.x == 0 && threadIdx.x < G_N) {
     const int k = threadIdx.x;
-    double acc = globals[k];
+    double acc = overwrite ? ((k < 2) ? 0.0 : ((k & 1) ? CUDART_INF : -CUDART_INF)) : globals[k];
     for (int r = 0; r < nranks; ++r) {
       const double o = packed[(long long)r * stride + 4 * n + k];
       if (k < 2) acc += o;
@@ -172,15 +218,13 @@ __global__ void reset_globals_kernel(double* g) {
   if (k < G_N) g[k] = (k < 2) ? 0.0 : ((k & 1) ? CUDART_INF : -CUDART_INF);
 }
 
-__global__ void reset_state_kernel(ChainState* st, long long n) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < n) {
-    ChainState z;
-    z.m = -CUDART_INF;
-    z.s = 0.0;
-    z.n = 0.0;
-    z.nnan = 0.0;
-    st[c] = z;
+// the whole packed block [n x (m, s, n, n_nan) | G_N scalars] in one launch
+__global__ void reset_packed_kernel(double* packed, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * n) packed[i] = ((i & 3) == 0) ? -CUDART_INF : 0.0;
+  else if (i < 4 * n + G_N) {
+    const int k = (int)(i - 4 * n);
+    packed[i] = (k < 2) ? 0.0 : ((k & 1) ? CUDART_INF : -CUDART_INF);
   }
 }
 
@@ -262,7 +306,8 @@ __device__ double block_lse(long long n, F f, double* sh) {
 
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(const ChainState* __restrict__ state, const double* __restrict__ globals,
-                long long nch, int shift_mode, double shift_in, double* __restrict__ out) {
+                long long nch, int shift_mode, double shift_in, const unsigned long long* __restrict__ guard,
+                double* __restrict__ out) {
   __shared__ double sh[FIN_THREADS / 32];
   hb_result* res = reinterpret_cast<hb_result*>(out);
   double* ln_inv_pc = out + sizeof(hb_result) / sizeof(double);
@@ -280,14 +325,16 @@ finalize_kernel(const ChainState* __restrict__ state, const double* __restrict__
                                                                      : -globals[G_ARGMIN];
   }
 
-  double nsum = 0.0, n2sum = 0.0;
+  double nsum = 0.0, n2sum = 0.0, nansum = 0.0;
   for (long long c = threadIdx.x; c < nch; c += FIN_THREADS) {
     const double n = state[c].n;
     nsum += n;
     n2sum += n * n;
+    nansum += state[c].nnan;
   }
   const double N = block_sum(nsum, sh);
   const double N2 = block_sum(n2sum, sh);
+  const double NNAN = block_sum(nansum, sh);
   const double lnN = log(N);
   auto L = [&](long long c) {
     const ChainState st = state[c];
@@ -330,7 +377,9 @@ finalize_kernel(const ChainState* __restrict__ state, const double* __restrict__
     res->lnpredictmax = globals[G_PREDMAX];
     res->lnpredictmin = globals[G_PREDMIN];
     res->nsamples_total = N;
-    res->reserved[0] = res->reserved[1] = res->reserved[2] = 0.0;
+    res->mean_nsamples_eff = (N - NNAN) / (double)nch;
+    res->guard_trips = guard ? (double)*guard : 0.0;
+    res->reserved = 0.0;
   }
 }
 
@@ -370,7 +419,9 @@ finalize_realspace_kernel(const double* __restrict__ S, const double* __restrict
     res->lnargmax = res->lnargmin = res->lnprobmax = res->lnprobmin = CUDART_NAN;
     res->lnpredictmax = res->lnpredictmin = CUDART_NAN;
     res->nsamples_total = N;
-    res->reserved[0] = res->reserved[1] = res->reserved[2] = 0.0;
+    res->mean_nsamples_eff = N / (double)nch;
+    res->guard_trips = 0.0;
+    res->reserved = 0.0;
   }
 }
 
@@ -397,12 +448,23 @@ int ensure_scratch(Accum* acc, long long nch, long long nflushers) {
   return HB_OK;
 }
 
+// every entry point that touches the accumulator on `st` orders itself behind a pending reset
+// (hb_accum_create / hb_accum_reset without a stream run it on the legacy default stream)
+int order_after_reset(Accum* acc, cudaStream_t st) {
+  if (acc->reset_pending) {
+    HB_CUDA(cudaStreamWaitEvent(st, acc->ev_reset, 0));
+    acc->reset_pending = false;
+  }
+  return HB_OK;
+}
+
 int launch_merge(Accum* acc, const FoldParams& p, long long chain_lo, long long nflushers,
                  cudaStream_t st) {
   const int threads = 256;
   const int blocks = (int)((p.nch + threads - 1) / threads);
   merge_kernel<<<blocks > 0 ? blocks : 1, threads, 0, st>>>(acc->state, acc->globals, p, chain_lo,
-                                                             nflushers);
+                                                             nflushers, acc->fresh_call ? 1 : 0);
+  acc->fresh_call = false;
   count_launch();
   HB_CUDA(cudaGetLastError());
   return HB_OK;
@@ -439,7 +501,15 @@ int prepare_fold(Accum* acc, const int64_t* start, long long chain_lo, long long
   return HB_OK;
 }
 
-int reset_call_scalars(Accum* acc, cudaStream_t st) {
+// First launch of an add_chains call: the per-call scalars start afresh.  The reset is folded into the
+// call's first merge_kernel (it overwrites instead of folding); a call without rows resets them here.
+int begin_call(Accum* acc, bool has_rows, cudaStream_t st) {
+  int rc = order_after_reset(acc, st);
+  if (rc) return rc;
+  if (has_rows) {
+    acc->fresh_call = true;
+    return HB_OK;
+  }
   reset_globals_kernel<<<1, 32, 0, st>>>(acc->globals);
   count_launch();
   HB_CUDA(cudaGetLastError());
@@ -492,15 +562,95 @@ int accumulate_precomputed_device(Accum* acc, const void* lnpred, int pd, const 
   return launch_acc(acc, (const double*)lnpred, (const double*)lnpost, start, chain_lo, chain_hi, a, b, st);
 }
 
+// ---- staging buffers: a per-process free list, borrowed for the duration of one host-input call ----
+static std::mutex g_stage_mu;
+static std::vector<Stage*> g_stage_free;
+
+static void stage_free_buffers(Stage* s) {
+  cudaSetDevice(s->device);
+  for (int i = 0; i < 2; ++i) {
+    if (s->dev[i]) cudaFree(s->dev[i]);
+    if (s->pin[i]) cudaFreeHost(s->pin[i]);
+    if (s->ev_copy[i]) cudaEventDestroy(s->ev_copy[i]);
+    if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
+  }
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  delete s;
+}
+
+Stage* stage_acquire(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    for (size_t i = 0; i < g_stage_free.size(); ++i) {
+      if (g_stage_free[i]->device == device) {
+        Stage* s = g_stage_free[i];
+        g_stage_free.erase(g_stage_free.begin() + i);
+        return s;
+      }
+    }
+  }
+  Stage* s = new Stage();
+  s->device = device;
+  bool ok = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) {
+    ok = cudaEventCreateWithFlags(&s->ev_copy[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    cuda_fail(cudaGetLastError(), "staging stream / events", __FILE__, __LINE__);
+    stage_free_buffers(s);
+    return nullptr;
+  }
+  return s;
+}
+
+void stage_release(Stage* s, cudaStream_t st) {
+  if (!s) return;
+  // nothing of this call may still be in flight when the buffers change hands (error paths included)
+  cudaStreamSynchronize(s->copy_stream);
+  cudaStreamSynchronize(st);
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  // at most two parked stages per process keep their buffers (double-buffered pinned + device chunks,
+  // <= ~0.7 GB each); hb_pool_trim() frees them
+  if (g_stage_free.size() < 2) g_stage_free.push_back(s);
+  else stage_free_buffers(s);
+}
+
 }  // namespace hb
 
 using namespace hb;
 
 // Released accumulators are parked here and handed out again for the same (device, nchains):
-// creating one costs several cudaMalloc / stream / event calls, which a per-call Evidence would
-// otherwise pay on every add_chains.
+// creating one costs several cudaMalloc / event calls, which a per-call Evidence would otherwise pay
+// on every add_chains.  They hold O(nchains + flushers) bytes only (staging lives in the Stage list);
+// on a miss with a full pool the oldest entry is evicted.
 static std::mutex g_pool_mu;
 static std::vector<Accum*> g_pool;
+constexpr size_t POOL_MAX = 8;
+
+static void accum_free(Accum* acc) {
+  cudaSetDevice(acc->device);
+  cudaFree(acc->packed);
+  cudaFree(acc->start_dev);
+  cudaFree(acc->recs);
+  cudaFree(acc->gpart);
+  cudaFree(acc->fin);
+  cudaFree(acc->guard);
+  if (acc->fin_host) cudaFreeHost(acc->fin_host);
+  if (acc->ev_reset) cudaEventDestroy(acc->ev_reset);
+  delete acc;
+}
+
+static int accum_reset_on(Accum* acc, cudaStream_t st) {
+  const int threads = 256;
+  const long long n = 4 * acc->nchains + G_N;
+  reset_packed_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(acc->packed, acc->nchains);
+  count_launch();
+  HB_CUDA(cudaGetLastError());
+  HB_CUDA(cudaMemsetAsync(acc->guard, 0, sizeof(unsigned long long), st));
+  acc->fresh_call = false;
+  return HB_OK;
+}
 
 extern "C" {
 
@@ -509,33 +659,39 @@ int hb_accum_create(int64_t nchains, int device, hb_accum** out) {
   HB_REQUIRE(nchains >= 1, "nchains must be greater than 0.");
   int rc = require_device(device);
   if (rc) return rc;
+  HB_CUDA(cudaSetDevice(device));
+  Accum* acc = nullptr;
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     for (size_t i = 0; i < g_pool.size(); ++i) {
       if (g_pool[i]->device == device && g_pool[i]->nchains == nchains) {
-        Accum* a = g_pool[i];
+        acc = g_pool[i];
         g_pool.erase(g_pool.begin() + i);
-        *out = reinterpret_cast<hb_accum*>(a);
-        HB_CUDA(cudaSetDevice(device));
-        return hb_accum_reset(*out);
+        break;
       }
     }
   }
-  Accum* acc = new Accum();
-  acc->device = device;
-  acc->nchains = nchains;
-  HB_CUDA(cudaSetDevice(device));
-  HB_CUDA(cudaMalloc(&acc->state, nchains * sizeof(ChainState)));
-  HB_CUDA(cudaMalloc(&acc->globals, G_N * sizeof(double)));
-  HB_CUDA(cudaMalloc(&acc->start_dev, (nchains + 1) * sizeof(long long)));
-  HB_CUDA(cudaMalloc(&acc->fin, sizeof(hb_result) + 4 * nchains * sizeof(double)));
-  HB_CUDA(cudaStreamCreateWithFlags(&acc->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
-    HB_CUDA(cudaEventCreateWithFlags(&acc->ev_copy[i], cudaEventDisableTiming));
-    HB_CUDA(cudaEventCreateWithFlags(&acc->ev_done[i], cudaEventDisableTiming));
+  if (!acc) {
+    acc = new Accum();
+    acc->device = device;
+    acc->nchains = nchains;
+    cudaError_t e = cudaMalloc(&acc->packed, (4 * nchains + G_N) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&acc->start_dev, (nchains + 1) * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&acc->fin, sizeof(hb_result) + 4 * nchains * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&acc->guard, sizeof(unsigned long long));
+    if (e == cudaSuccess)
+      e = cudaHostAlloc(reinterpret_cast<void**>(&acc->fin_host), sizeof(hb_result) + 4 * nchains * sizeof(double),
+                        cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&acc->ev_reset, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      accum_free(acc);
+      return cuda_fail(e, "accumulator allocation", __FILE__, __LINE__);
+    }
+    acc->state = reinterpret_cast<ChainState*>(acc->packed);
+    acc->globals = acc->packed + 4 * nchains;
   }
   *out = reinterpret_cast<hb_accum*>(acc);
-  return hb_accum_reset(*out);
+  return hb_accum_reset(*out, nullptr);
 }
 
 int hb_accum_destroy(hb_accum* h) {
@@ -543,40 +699,45 @@ int hb_accum_destroy(hb_accum* h) {
   Accum* acc = reinterpret_cast<Accum*>(h);
   cudaSetDevice(acc->device);
   cudaDeviceSynchronize();
+  Accum* evict = nullptr;
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (g_pool.size() < 8) {
-      g_pool.push_back(acc);
-      return HB_OK;
+    if (g_pool.size() >= POOL_MAX) {
+      evict = g_pool.front();
+      g_pool.erase(g_pool.begin());
     }
+    g_pool.push_back(acc);
   }
-  cudaFree(acc->state);
-  cudaFree(acc->globals);
-  cudaFree(acc->start_dev);
-  cudaFree(acc->recs);
-  cudaFree(acc->gpart);
-  cudaFree(acc->fin);
-  for (int i = 0; i < 2; ++i) {
-    if (acc->dev[i]) cudaFree(acc->dev[i]);
-    if (acc->pin[i]) cudaFreeHost(acc->pin[i]);
-    if (acc->ev_copy[i]) cudaEventDestroy(acc->ev_copy[i]);
-    if (acc->ev_done[i]) cudaEventDestroy(acc->ev_done[i]);
-  }
-  if (acc->copy_stream) cudaStreamDestroy(acc->copy_stream);
-  delete acc;
+  if (evict) accum_free(evict);
   return HB_OK;
 }
 
-int hb_accum_reset(hb_accum* h) {
+int hb_pool_trim(void) {
+  std::vector<Accum*> accs;
+  std::vector<Stage*> stages;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    accs.swap(g_pool);
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    stages.swap(g_stage_free);
+  }
+  for (Accum* a : accs) accum_free(a);
+  for (Stage* s : stages) stage_free_buffers(s);
+  return HB_OK;
+}
+
+int hb_accum_reset(hb_accum* h, void* stream) {
   HB_REQUIRE(h != nullptr, "hb_accum_reset: NULL handle");
   Accum* acc = reinterpret_cast<Accum*>(h);
   HB_CUDA(cudaSetDevice(acc->device));
-  const int threads = 256;
-  reset_state_kernel<<<(int)((acc->nchains + threads - 1) / threads), threads>>>(acc->state,
-                                                                                 acc->nchains);
-  reset_globals_kernel<<<1, 32>>>(acc->globals);
-  count_launch(2);
-  HB_CUDA(cudaGetLastError());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = accum_reset_on(acc, st);
+  if (rc) return rc;
+  // later calls may arrive on any stream: they wait on this event (order_after_reset)
+  HB_CUDA(cudaEventRecord(acc->ev_reset, st));
+  acc->reset_pending = true;
   return HB_OK;
 }
 
@@ -594,106 +755,113 @@ int hb_accumulate_precomputed(hb_accum* h, const void* lnpred, int lnpred_dtype,
              "dtype must be HB_F32 or HB_F64");
   HB_CUDA(cudaSetDevice(acc->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (flags & HB_ACC_NEW_CALL) {
-    int rc = reset_call_scalars(acc, st);
-    if (rc) return rc;
-  }
   const long long nrows = start_indices[chain_hi] - start_indices[chain_lo];
-  if (nrows == 0 || chain_lo == chain_hi) return HB_OK;
+  const bool has_rows = nrows > 0 && chain_lo < chain_hi;
+  int rc = (flags & HB_ACC_NEW_CALL) ? begin_call(acc, has_rows, st) : order_after_reset(acc, st);
+  if (rc) return rc;
+  if (!has_rows) return HB_OK;
   HB_REQUIRE(lnpred != nullptr && ln_posterior != nullptr, "NULL input buffer");
   if (mem == HB_MEM_DEVICE)
     return accumulate_precomputed_device(acc, lnpred, lnpred_dtype, ln_posterior, lp_dtype,
                                          start_indices, chain_lo, chain_hi, 0, nrows, st);
-  // HOST buffers: chunked, double-buffered staging overlapped with the fold kernel
-  if (!is_pinned_host(lnpred) || !is_pinned_host(ln_posterior)) {
-    // pageable memory: host threads convert to float32 into pinned staging (see hb_accumulate_flow)
-    const long long chunkp = 1LL << 23;
-    const size_t offl = (size_t)chunkp * 4;
-    int rcp = ensure_stage(acc, 2 * offl);
-    if (rcp) return rcp;
-    rcp = ensure_pinned(acc, 2 * offl);
-    if (rcp) return rcp;
-    const int nth = host_threads();
-    int ip = 0;
-    for (long long a = 0; a < nrows; a += chunkp, ++ip) {
-      const long long b = (a + chunkp < nrows) ? a + chunkp : nrows;
-      const int sl = ip & 1;
-      char* hp = static_cast<char*>(acc->pin[sl]);
-      char* d = static_cast<char*>(acc->dev[sl]);
-      HB_CUDA(cudaEventSynchronize(acc->ev_copy[sl]));
-      if (lnpred_dtype == HB_F64) convert_rows((const double*)lnpred, 1, 1, a, b, (float*)hp, nth);
-      else convert_rows((const float*)lnpred, 1, 1, a, b, (float*)hp, nth);
-      if (lp_dtype == HB_F64) convert_rows((const double*)ln_posterior, 1, 1, a, b, (float*)(hp + offl), nth);
-      else convert_rows((const float*)ln_posterior, 1, 1, a, b, (float*)(hp + offl), nth);
-      HB_CUDA(cudaStreamWaitEvent(acc->copy_stream, acc->ev_done[sl], 0));
-      HB_CUDA(cudaMemcpyAsync(d, hp, offl + (size_t)(b - a) * 4, cudaMemcpyHostToDevice, acc->copy_stream));
-      HB_CUDA(cudaEventRecord(acc->ev_copy[sl], acc->copy_stream));
-      HB_CUDA(cudaStreamWaitEvent(st, acc->ev_copy[sl], 0));
-      rcp = accumulate_precomputed_device(acc, d, HB_F32, d + offl, HB_F32, start_indices, chain_lo, chain_hi,
-                                          a, b, st);
-      if (rcp) return rcp;
-      HB_CUDA(cudaEventRecord(acc->ev_done[sl], st));
-    }
-    HB_CUDA(cudaStreamSynchronize(st));
-    return HB_OK;
-  }
+  // HOST buffers: chunked, double-buffered staging overlapped with the fold kernel.  Pinned buffers are
+  // copied straight from the caller's memory; pageable ones go through pinned staging filled by host threads.
+  // The element types travel unchanged (float64 stays float64: the kernel forms lnpred - ln_posterior in
+  // double before rounding to float32, as numpy does in the reference's per-sample branch,
+  // harmonic/evidence.py:285-303).
+  StageLease lease(acc->device, st);
+  Stage* sg = lease.get();
+  if (!sg) return HB_ERR_CUDA;
+  const bool pinned = is_pinned_host(lnpred) && is_pinned_host(ln_posterior);
   const size_t es_p = lnpred_dtype == HB_F32 ? 4 : 8, es_l = lp_dtype == HB_F32 ? 4 : 8;
-  const long long chunk = 1LL << 24;  // rows per chunk
-  int rc = ensure_stage(acc, (size_t)chunk * (es_p + es_l));
+  const long long chunk = pinned ? (1LL << 24) : (1LL << 22);  // rows per chunk
+  const size_t off_l = (size_t)chunk * es_p;
+  rc = ensure_stage(sg, (size_t)chunk * (es_p + es_l));
   if (rc) return rc;
+  if (!pinned) {
+    rc = ensure_pinned(sg, (size_t)chunk * (es_p + es_l));
+    if (rc) return rc;
+  }
+  const int nth = host_threads();
   int i = 0;
   for (long long a = 0; a < nrows; a += chunk, ++i) {
     const long long b = (a + chunk < nrows) ? a + chunk : nrows;
     const int sl = i & 1;
-    char* d = static_cast<char*>(acc->dev[sl]);
-    char* dl = d + (size_t)chunk * es_p;
-    HB_CUDA(cudaStreamWaitEvent(acc->copy_stream, acc->ev_done[sl], 0));
-    HB_CUDA(cudaMemcpyAsync(d, (const char*)lnpred + a * es_p, (b - a) * es_p,
-                            cudaMemcpyHostToDevice, acc->copy_stream));
-    HB_CUDA(cudaMemcpyAsync(dl, (const char*)ln_posterior + a * es_l, (b - a) * es_l,
-                            cudaMemcpyHostToDevice, acc->copy_stream));
-    HB_CUDA(cudaEventRecord(acc->ev_copy[sl], acc->copy_stream));
-    HB_CUDA(cudaStreamWaitEvent(st, acc->ev_copy[sl], 0));
+    char* d = static_cast<char*>(sg->dev[sl]);
+    char* dl = d + off_l;
+    if (pinned) {
+      HB_CUDA(cudaStreamWaitEvent(sg->copy_stream, sg->ev_done[sl], 0));
+      HB_CUDA(cudaMemcpyAsync(d, (const char*)lnpred + a * es_p, (b - a) * es_p, cudaMemcpyHostToDevice,
+                              sg->copy_stream));
+      HB_CUDA(cudaMemcpyAsync(dl, (const char*)ln_posterior + a * es_l, (b - a) * es_l, cudaMemcpyHostToDevice,
+                              sg->copy_stream));
+    } else {
+      char* hp = static_cast<char*>(sg->pin[sl]);
+      HB_CUDA(cudaEventSynchronize(sg->ev_copy[sl]));  // the pinned slot's previous copy has left
+      copy_bytes((const char*)lnpred + a * es_p, hp, (size_t)(b - a) * es_p, nth);
+      copy_bytes((const char*)ln_posterior + a * es_l, hp + off_l, (size_t)(b - a) * es_l, nth);
+      HB_CUDA(cudaStreamWaitEvent(sg->copy_stream, sg->ev_done[sl], 0));
+      HB_CUDA(cudaMemcpyAsync(d, hp, off_l + (size_t)(b - a) * es_l, cudaMemcpyHostToDevice, sg->copy_stream));
+    }
+    HB_CUDA(cudaEventRecord(sg->ev_copy[sl], sg->copy_stream));
+    HB_CUDA(cudaStreamWaitEvent(st, sg->ev_copy[sl], 0));
     rc = accumulate_precomputed_device(acc, d, lnpred_dtype, dl, lp_dtype, start_indices, chain_lo,
                                        chain_hi, a, b, st);
     if (rc) return rc;
-    HB_CUDA(cudaEventRecord(acc->ev_done[sl], st));
+    HB_CUDA(cudaEventRecord(sg->ev_done[sl], st));
   }
   HB_CUDA(cudaStreamSynchronize(st));
   return HB_OK;
 }
 
-int hb_accum_export(hb_accum* h, double* partials, double* globals) {
+int hb_accum_export(hb_accum* h, double* partials, double* globals, void* stream) {
   HB_REQUIRE(h != nullptr, "hb_accum_export: NULL handle");
   Accum* acc = reinterpret_cast<Accum*>(h);
   HB_CUDA(cudaSetDevice(acc->device));
-  HB_CUDA(cudaDeviceSynchronize());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = order_after_reset(acc, st);
+  if (rc) return rc;
   if (partials)
-    HB_CUDA(cudaMemcpy(partials, acc->state, acc->nchains * sizeof(ChainState),
-                       cudaMemcpyDeviceToHost));
-  if (globals) HB_CUDA(cudaMemcpy(globals, acc->globals, G_N * sizeof(double), cudaMemcpyDeviceToHost));
+    HB_CUDA(cudaMemcpyAsync(partials, acc->state, acc->nchains * sizeof(ChainState), cudaMemcpyDeviceToHost, st));
+  if (globals)
+    HB_CUDA(cudaMemcpyAsync(globals, acc->globals, G_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HB_CUDA(cudaStreamSynchronize(st));
   return HB_OK;
 }
 
-int hb_accum_merge(hb_accum* h, const double* partials, const double* globals) {
+int hb_accum_merge(hb_accum* h, const double* partials, const double* globals, void* stream) {
   HB_REQUIRE(h != nullptr && partials != nullptr, "hb_accum_merge: NULL argument");
   Accum* acc = reinterpret_cast<Accum*>(h);
   HB_CUDA(cudaSetDevice(acc->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = order_after_reset(acc, st);
+  if (rc) return rc;
   double *dpart = nullptr, *dg = nullptr;
-  HB_CUDA(cudaMalloc(&dpart, acc->nchains * 4 * sizeof(double)));
-  HB_CUDA(cudaMemcpy(dpart, partials, acc->nchains * 4 * sizeof(double), cudaMemcpyHostToDevice));
-  if (globals) {
-    HB_CUDA(cudaMalloc(&dg, G_N * sizeof(double)));
-    HB_CUDA(cudaMemcpy(dg, globals, G_N * sizeof(double), cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMalloc(&dpart, (acc->nchains * 4 + G_N) * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(dpart, partials, acc->nchains * 4 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && globals) {
+    dg = dpart + acc->nchains * 4;
+    e = cudaMemcpyAsync(dg, globals, G_N * sizeof(double), cudaMemcpyHostToDevice, st);
   }
-  const int threads = 256;
-  merge_partials_kernel<<<(int)((acc->nchains + threads - 1) / threads), threads>>>(
-      acc->state, acc->globals, dpart, dg, acc->nchains);
-  count_launch();
-  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) {
+    const int threads = 256;
+    merge_partials_kernel<<<(int)((acc->nchains + threads - 1) / threads), threads, 0, st>>>(
+        acc->state, acc->globals, dpart, dg, acc->nchains);
+    count_launch();
+    e = cudaGetLastError();
+  }
+  const cudaError_t e2 = cudaStreamSynchronize(st);
   cudaFree(dpart);
-  if (dg) cudaFree(dg);
   HB_CUDA(e);
+  HB_CUDA(e2);
+  return HB_OK;
+}
+
+int hb_accum_packed_ptr(hb_accum* h, double** out, int64_t* n_doubles) {
+  HB_REQUIRE(h != nullptr && out != nullptr, "hb_accum_packed_ptr: NULL argument");
+  Accum* acc = reinterpret_cast<Accum*>(h);
+  *out = acc->packed;
+  if (n_doubles) *n_doubles = 4 * acc->nchains + G_N;
   return HB_OK;
 }
 
@@ -702,20 +870,23 @@ int hb_accum_pack(hb_accum* h, double* dst, int mem, void* stream) {
   Accum* acc = reinterpret_cast<Accum*>(h);
   HB_CUDA(cudaSetDevice(acc->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = order_after_reset(acc, st);
+  if (rc) return rc;
   const cudaMemcpyKind kind = mem == HB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  HB_CUDA(cudaMemcpyAsync(dst, acc->state, acc->nchains * sizeof(ChainState), kind, st));
-  HB_CUDA(cudaMemcpyAsync(dst + 4 * acc->nchains, acc->globals, G_N * sizeof(double), kind, st));
+  HB_CUDA(cudaMemcpyAsync(dst, acc->packed, (4 * acc->nchains + G_N) * sizeof(double), kind, st));
   if (mem != HB_MEM_DEVICE) HB_CUDA(cudaStreamSynchronize(st));
   return HB_OK;
 }
 
 int hb_accum_merge_packed(hb_accum* h, int nranks, const double* packed, int64_t stride, int mem,
-                          void* stream) {
+                          int flags, void* stream) {
   HB_REQUIRE(h != nullptr && packed != nullptr && nranks >= 1, "hb_accum_merge_packed: bad argument");
   Accum* acc = reinterpret_cast<Accum*>(h);
   HB_REQUIRE(stride >= 4 * acc->nchains + G_N, "hb_accum_merge_packed: stride too small");
   HB_CUDA(cudaSetDevice(acc->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = order_after_reset(acc, st);
+  if (rc) return rc;
   const double* src = packed;
   double* tmp = nullptr;
   if (mem != HB_MEM_DEVICE) {
@@ -730,7 +901,7 @@ int hb_accum_merge_packed(hb_accum* h, int nranks, const double* packed, int64_t
   }
   const int threads = 256;
   merge_packed_kernel<<<(int)((acc->nchains + threads - 1) / threads), threads, 0, st>>>(
-      acc->state, acc->globals, src, stride, nranks, acc->nchains);
+      acc->state, acc->globals, src, stride, nranks, acc->nchains, (flags & HB_MERGE_OVERWRITE) ? 1 : 0);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (tmp) {
@@ -743,27 +914,51 @@ int hb_accum_merge_packed(hb_accum* h, int nranks, const double* packed, int64_t
 
 int hb_finalize(hb_accum* h, int shift_mode, double shift_value_in, hb_result* out,
                 double* ln_inv_per_chain, double* running_sum, double* nsamples_per_chain,
-                double* nsamples_eff_per_chain) {
+                double* nsamples_eff_per_chain, void* stream) {
   HB_REQUIRE(h != nullptr && out != nullptr, "hb_finalize: NULL argument");
   HB_REQUIRE(shift_mode >= HB_MEAN_SHIFT && shift_mode <= HB_ABS_MAX_SHIFT, "unknown shift mode");
   Accum* acc = reinterpret_cast<Accum*>(h);
   HB_CUDA(cudaSetDevice(acc->device));
-  HB_CUDA(cudaDeviceSynchronize());  // accumulate launches may sit on caller streams
-  finalize_kernel<<<1, FIN_THREADS>>>(acc->state, acc->globals, acc->nchains, shift_mode,
-                                      shift_value_in, acc->fin);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = order_after_reset(acc, st);
+  if (rc) return rc;
+  // stream-ordered behind the accumulate / merge launches of the same stream: no device-wide sync
+  finalize_kernel<<<1, FIN_THREADS, 0, st>>>(acc->state, acc->globals, acc->nchains, shift_mode,
+                                             shift_value_in, acc->guard, acc->fin);
   count_launch();
   HB_CUDA(cudaGetLastError());
   const size_t off = sizeof(hb_result) / sizeof(double);
   const size_t n = (size_t)acc->nchains;
   const bool want_arrays = ln_inv_per_chain || running_sum || nsamples_per_chain || nsamples_eff_per_chain;
-  static thread_local std::vector<double> host;
-  host.resize(off + (want_arrays ? 4 * n : 0));
-  HB_CUDA(cudaMemcpy(host.data(), acc->fin, host.size() * sizeof(double), cudaMemcpyDeviceToHost));  // one D2H
-  memcpy(out, host.data(), sizeof(hb_result));
-  if (ln_inv_per_chain) memcpy(ln_inv_per_chain, host.data() + off, n * sizeof(double));
-  if (running_sum) memcpy(running_sum, host.data() + off + n, n * sizeof(double));
-  if (nsamples_per_chain) memcpy(nsamples_per_chain, host.data() + off + 2 * n, n * sizeof(double));
-  if (nsamples_eff_per_chain) memcpy(nsamples_eff_per_chain, host.data() + off + 3 * n, n * sizeof(double));
+  // one D2H into the pinned mirror: the 128-byte result alone unless the per-chain arrays are asked for
+  // (hb_finalize_arrays fetches them later)
+  HB_CUDA(cudaMemcpyAsync(acc->fin_host, acc->fin, (off + (want_arrays ? 4 * n : 0)) * sizeof(double),
+                          cudaMemcpyDeviceToHost, st));
+  HB_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, acc->fin_host, sizeof(hb_result));
+  const double* host = acc->fin_host;
+  if (ln_inv_per_chain) memcpy(ln_inv_per_chain, host + off, n * sizeof(double));
+  if (running_sum) memcpy(running_sum, host + off + n, n * sizeof(double));
+  if (nsamples_per_chain) memcpy(nsamples_per_chain, host + off + 2 * n, n * sizeof(double));
+  if (nsamples_eff_per_chain) memcpy(nsamples_eff_per_chain, host + off + 3 * n, n * sizeof(double));
+  return HB_OK;
+}
+
+int hb_finalize_arrays(hb_accum* h, double* ln_inv_per_chain, double* running_sum, double* nsamples_per_chain,
+                       double* nsamples_eff_per_chain, void* stream) {
+  HB_REQUIRE(h != nullptr, "hb_finalize_arrays: NULL handle");
+  Accum* acc = reinterpret_cast<Accum*>(h);
+  HB_CUDA(cudaSetDevice(acc->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t off = sizeof(hb_result) / sizeof(double);
+  const size_t n = (size_t)acc->nchains;
+  HB_CUDA(cudaMemcpyAsync(acc->fin_host + off, acc->fin + off, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HB_CUDA(cudaStreamSynchronize(st));
+  const double* host = acc->fin_host;
+  if (ln_inv_per_chain) memcpy(ln_inv_per_chain, host + off, n * sizeof(double));
+  if (running_sum) memcpy(running_sum, host + off + n, n * sizeof(double));
+  if (nsamples_per_chain) memcpy(nsamples_per_chain, host + off + 2 * n, n * sizeof(double));
+  if (nsamples_eff_per_chain) memcpy(nsamples_eff_per_chain, host + off + 3 * n, n * sizeof(double));
   return HB_OK;
 }
 

@@ -3,7 +3,13 @@
 #include <math.h>
 #include <string.h>
 
+#include <sched.h>
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <atomic>
+#include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -14,9 +20,17 @@ namespace hb {
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+
+// kernel timing (bench.py's roofline block): one event pair per device, guarded by a mutex -- several host
+// threads may drive handles on the same device
+constexpr int MAX_DEV = 64;
+struct DevTiming {
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool pending = false;
+};
+static std::mutex g_timing_mu;
 static bool g_timing = false;
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-static bool g_timing_pending = false;
+static DevTiming g_dev_timing[MAX_DEV];
 
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch(int n) { g_launches += n; }
@@ -27,18 +41,40 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return HB_ERR_CUDA;
 }
 
-void timing_begin(cudaStream_t st) {
-  if (!g_timing) return;
-  if (!g_ev0) {
-    cudaEventCreate(&g_ev0);
-    cudaEventCreate(&g_ev1);
+static DevTiming* timing_slot() {  // caller holds g_timing_mu
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+  DevTiming* t = &g_dev_timing[dev];
+  if (!t->ev0) {
+    if (cudaEventCreate(&t->ev0) != cudaSuccess || cudaEventCreate(&t->ev1) != cudaSuccess) return nullptr;
   }
-  cudaEventRecord(g_ev0, st);
+  return t;
+}
+void timing_begin(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (!g_timing) return;
+  if (DevTiming* t = timing_slot()) cudaEventRecord(t->ev0, st);
 }
 void timing_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   if (!g_timing) return;
-  cudaEventRecord(g_ev1, st);
-  g_timing_pending = true;
+  if (DevTiming* t = timing_slot()) {
+    cudaEventRecord(t->ev1, st);
+    t->pending = true;
+  }
+}
+
+int host_threads() {
+  static const int forced = [] {
+    const char* e = getenv("HB_HOST_THREADS");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0) return forced;
+  int n = 0;
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+  if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  return n > 16 ? 16 : (n < 1 ? 1 : n);
 }
 
 int require_device(int device) {
@@ -58,7 +94,7 @@ int require_device(int device) {
   }
   cudaDeviceProp prop;
   HB_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
+  if (prop.major != 10 || prop.minor != 0) {  // the binary holds sm_100a code only
     set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
               "; libharmonic_b200 is built for sm_100a only");
     return HB_ERR_NO_DEVICE;
@@ -67,7 +103,7 @@ int require_device(int device) {
   return HB_OK;
 }
 
-int ensure_pinned(Accum* acc, size_t bytes_per_slot) {
+int ensure_pinned(Stage* acc, size_t bytes_per_slot) {
   if (bytes_per_slot <= acc->pin_cap) return HB_OK;
   for (int i = 0; i < 2; ++i) {
     if (acc->pin[i]) cudaFreeHost(acc->pin[i]);
@@ -79,7 +115,7 @@ int ensure_pinned(Accum* acc, size_t bytes_per_slot) {
   return HB_OK;
 }
 
-int ensure_stage(Accum* acc, size_t bytes_per_slot) {
+int ensure_stage(Stage* acc, size_t bytes_per_slot) {
   if (bytes_per_slot <= acc->stage_cap) return HB_OK;
   for (int i = 0; i < 2; ++i) {
     if (acc->dev[i]) cudaFree(acc->dev[i]);
@@ -122,33 +158,36 @@ static int accumulate_flow_pageable(Accum* acc, Flow* f, float temperature, cons
   const size_t off_l = (((size_t)chunk * D * 4) + 255) & ~(size_t)255;
   const size_t off_o = (off_l + (size_t)chunk * 4 + 255) & ~(size_t)255;
   const size_t slot = off_o + (lnpred_out ? (size_t)chunk * 4 : 0) + 256;
-  int rc = ensure_stage(acc, slot);
+  StageLease lease(acc->device, st);
+  Stage* sg = lease.get();
+  if (!sg) return HB_ERR_CUDA;
+  int rc = ensure_stage(sg, slot);
   if (rc) return rc;
-  rc = ensure_pinned(acc, off_o + 256);
+  rc = ensure_pinned(sg, off_o + 256);
   if (rc) return rc;
   int i = 0;
   for (long long a = 0; a < nrows; a += chunk, ++i) {
     const long long b = (a + chunk < nrows) ? a + chunk : nrows;
     const int sl = i & 1;
-    char* hp = static_cast<char*>(acc->pin[sl]);
-    char* dxp = static_cast<char*>(acc->dev[sl]);
+    char* hp = static_cast<char*>(sg->pin[sl]);
+    char* dxp = static_cast<char*>(sg->dev[sl]);
     // the pinned slot is free once the H2D copy of chunk i-2 has been consumed
-    HB_CUDA(cudaEventSynchronize(acc->ev_copy[sl]));
+    HB_CUDA(cudaEventSynchronize(sg->ev_copy[sl]));
     if (x_dtype == HB_F64) convert_rows((const double*)x, ld, D, a, b, reinterpret_cast<float*>(hp), nthreads);
     else convert_rows((const float*)x, ld, D, a, b, reinterpret_cast<float*>(hp), nthreads);
     if (lp_dtype == HB_F64) convert_rows((const double*)lnpost, 1, 1, a, b, reinterpret_cast<float*>(hp + off_l), nthreads);
     else convert_rows((const float*)lnpost, 1, 1, a, b, reinterpret_cast<float*>(hp + off_l), nthreads);
-    HB_CUDA(cudaStreamWaitEvent(acc->copy_stream, acc->ev_done[sl], 0));  // device slot free
-    HB_CUDA(cudaMemcpyAsync(dxp, hp, off_l + (size_t)(b - a) * 4, cudaMemcpyHostToDevice, acc->copy_stream));
-    HB_CUDA(cudaEventRecord(acc->ev_copy[sl], acc->copy_stream));
-    HB_CUDA(cudaStreamWaitEvent(st, acc->ev_copy[sl], 0));
+    HB_CUDA(cudaStreamWaitEvent(sg->copy_stream, sg->ev_done[sl], 0));  // device slot free
+    HB_CUDA(cudaMemcpyAsync(dxp, hp, off_l + (size_t)(b - a) * 4, cudaMemcpyHostToDevice, sg->copy_stream));
+    HB_CUDA(cudaEventRecord(sg->ev_copy[sl], sg->copy_stream));
+    HB_CUDA(cudaStreamWaitEvent(st, sg->ev_copy[sl], 0));
     float* dop = lnpred_out ? reinterpret_cast<float*>(dxp + off_o) : nullptr;
     rc = flow_run(f, temperature, dxp, HB_F32, D, b - a, dxp + off_l, HB_F32, dop, acc, start_indices,
                   chain_lo, chain_hi, a, b, st);
     if (rc) return rc;
     if (dop)
       HB_CUDA(cudaMemcpyAsync(lnpred_out + a, dop, (size_t)(b - a) * 4, cudaMemcpyDeviceToHost, st));
-    HB_CUDA(cudaEventRecord(acc->ev_done[sl], st));
+    HB_CUDA(cudaEventRecord(sg->ev_done[sl], st));
   }
   HB_CUDA(cudaStreamSynchronize(st));
   return HB_OK;
@@ -174,7 +213,7 @@ int hb_device_count(void) {
   int ok = 0;
   for (int i = 0; i < n; ++i) {
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++ok;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10 && prop.minor == 0) ++ok;
   }
   if (ok > 0) cached = ok;
   return ok;
@@ -183,15 +222,98 @@ int hb_device_count(void) {
 int64_t hb_launch_count(void) { return g_launches.load(); }
 
 int hb_set_kernel_timing(int on) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   g_timing = on != 0;
   return HB_OK;
 }
-double hb_last_kernel_ms(void) {
-  if (!g_timing_pending || !g_ev0) return -1.0;
+double hb_last_kernel_ms(int device) {
+  cudaEvent_t e0, e1;
+  {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (device < 0 || device >= MAX_DEV) return -1.0;
+    const DevTiming& t = g_dev_timing[device];
+    if (!t.pending || !t.ev0) return -1.0;
+    e0 = t.ev0;
+    e1 = t.ev1;
+  }
   float ms = 0.f;
-  if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.0;
-  if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.0;
+  if (cudaEventSynchronize(e1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) return -1.0;
   return (double)ms;
+}
+
+// Pin the calling thread (and the staging threads it spawns later) to the CPUs of the NUMA node the GPU
+// hangs off, read from sysfs; pinned staging buffers allocated afterwards land on that node (first touch).
+// Returns the number of CPUs bound, 0 when the topology is not exposed (nothing changed).
+int hb_bind_host_to_device_node(int device) {
+  char bus[32];
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  for (char* c = bus; *c; ++c)
+    if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* fh = fopen(path, "r");
+  if (!fh) return 0;
+  int node = -1;
+  const int got = fscanf(fh, "%d", &node);
+  fclose(fh);
+  if (got != 1 || node < 0) return 0;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  fh = fopen(path, "r");
+  if (!fh) return 0;
+  char list[4096];
+  const bool ok = fgets(list, sizeof(list), fh) != nullptr;
+  fclose(fh);
+  if (!ok) return 0;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int ncpu = 0;
+  for (char* p = list; *p;) {  // "0-15,32-47"
+    char* end;
+    const long a = strtol(p, &end, 10);
+    if (end == p) break;
+    long b = a;
+    p = end;
+    if (*p == '-') {
+      b = strtol(p + 1, &end, 10);
+      p = end;
+    }
+    for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+      CPU_SET((int)c, &set);
+      ++ncpu;
+    }
+    if (*p == ',') ++p;
+    else break;
+  }
+  if (ncpu == 0) return 0;
+  cpu_set_t cur, both;
+  if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {  // never widen what the launcher allowed
+    CPU_AND(&both, &cur, &set);
+    if (CPU_COUNT(&both) == 0) return 0;
+    set = both;
+    ncpu = CPU_COUNT(&set);
+  }
+  if (sched_setaffinity(0, sizeof(set), &set) != 0) return 0;
+  return ncpu;
+}
+
+// STREAM-style host copy rate (GB/s, read + write bytes) with `threads` workers over `bytes` per pass: the
+// ceiling of the host-staged end-to-end path (bench.py reports it next to e2e).
+double hb_host_copy_gbs(size_t bytes, int threads) {
+  if (bytes < (1u << 20) || threads < 1) return 0.0;
+  std::vector<char> src(bytes, 1), dst(bytes, 0);
+  copy_bytes(src.data(), dst.data(), bytes, threads);  // warm / fault in
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    const auto t0 = std::chrono::steady_clock::now();
+    copy_bytes(src.data(), dst.data(), bytes, threads);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (dt > 0) best = std::max(best, 2.0 * (double)bytes / dt / 1e9);
+  }
+  return best;
 }
 
 size_t hb_flow_weight_count(const hb_flow_desc* ds) {
@@ -442,12 +564,11 @@ int hb_accumulate_flow(hb_accum* ha, hb_flow* hf, float temperature, const void*
              "dtype must be HB_F32 or HB_F64");
   HB_CUDA(cudaSetDevice(acc->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (flags & HB_ACC_NEW_CALL) {
-    int rc = reset_call_scalars(acc, st);
-    if (rc) return rc;
-  }
   const long long nrows = start_indices[chain_hi] - start_indices[chain_lo];
-  if (nrows == 0 || chain_lo == chain_hi) return HB_OK;
+  const bool has_rows = nrows > 0 && chain_lo < chain_hi;
+  int rc = (flags & HB_ACC_NEW_CALL) ? begin_call(acc, has_rows, st) : order_after_reset(acc, st);
+  if (rc) return rc;
+  if (!has_rows) return HB_OK;
   HB_REQUIRE(x != nullptr && ln_posterior != nullptr, "NULL input buffer");
   if (mem == HB_MEM_DEVICE)
     return flow_run(f, temperature, x, x_dtype, ld, nrows, ln_posterior, lp_dtype, lnpred_out, acc,
@@ -468,28 +589,31 @@ int hb_accumulate_flow(hb_accum* ha, hb_flow* hf, float temperature, const void*
   if (chunk > nrows) chunk = ((nrows + 255) / 256) * 256;
   const size_t off_l = (((size_t)chunk * ld * es_x) + 255) & ~(size_t)255;
   const size_t off_o = (off_l + (size_t)chunk * es_l + 255) & ~(size_t)255;
-  int rc = ensure_stage(acc, off_o + (lnpred_out ? (size_t)chunk * 4 : 0) + 256);
+  StageLease lease(acc->device, st);
+  Stage* sg = lease.get();
+  if (!sg) return HB_ERR_CUDA;
+  rc = ensure_stage(sg, off_o + (lnpred_out ? (size_t)chunk * 4 : 0) + 256);
   if (rc) return rc;
   int i = 0;
   for (long long a = 0; a < nrows; a += chunk, ++i) {
     const long long b = (a + chunk < nrows) ? a + chunk : nrows;
     const int sl = i & 1;
-    char* dxp = static_cast<char*>(acc->dev[sl]);
+    char* dxp = static_cast<char*>(sg->dev[sl]);
     char* dlp = dxp + off_l;
     float* dop = lnpred_out ? reinterpret_cast<float*>(dxp + off_o) : nullptr;
-    HB_CUDA(cudaStreamWaitEvent(acc->copy_stream, acc->ev_done[sl], 0));
+    HB_CUDA(cudaStreamWaitEvent(sg->copy_stream, sg->ev_done[sl], 0));
     HB_CUDA(cudaMemcpyAsync(dxp, (const char*)x + (size_t)a * ld * es_x, (size_t)(b - a) * ld * es_x,
-                            cudaMemcpyHostToDevice, acc->copy_stream));
+                            cudaMemcpyHostToDevice, sg->copy_stream));
     HB_CUDA(cudaMemcpyAsync(dlp, (const char*)ln_posterior + (size_t)a * es_l, (size_t)(b - a) * es_l,
-                            cudaMemcpyHostToDevice, acc->copy_stream));
-    HB_CUDA(cudaEventRecord(acc->ev_copy[sl], acc->copy_stream));
-    HB_CUDA(cudaStreamWaitEvent(st, acc->ev_copy[sl], 0));
+                            cudaMemcpyHostToDevice, sg->copy_stream));
+    HB_CUDA(cudaEventRecord(sg->ev_copy[sl], sg->copy_stream));
+    HB_CUDA(cudaStreamWaitEvent(st, sg->ev_copy[sl], 0));
     rc = flow_run(f, temperature, dxp, x_dtype, ld, b - a, dlp, lp_dtype, dop, acc, start_indices,
                   chain_lo, chain_hi, a, b, st);
     if (rc) return rc;
     if (dop)
       HB_CUDA(cudaMemcpyAsync(lnpred_out + a, dop, (size_t)(b - a) * 4, cudaMemcpyDeviceToHost, st));
-    HB_CUDA(cudaEventRecord(acc->ev_done[sl], st));
+    HB_CUDA(cudaEventRecord(sg->ev_done[sl], st));
   }
   HB_CUDA(cudaStreamSynchronize(st));
   return HB_OK;

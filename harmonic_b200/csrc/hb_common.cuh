@@ -113,8 +113,9 @@ struct Fold {
     }
   }
 
-  __device__ __forceinline__ void sample(float lnpred, float lnpost) {
-    float a = lnpred - lnpost;
+  // `diff` (optional): lnpred - lnpost already formed at higher precision by the caller (float64 inputs)
+  __device__ __forceinline__ void sample(float lnpred, float lnpost, const float* diff = nullptr) {
+    float a = diff ? *diff : lnpred - lnpost;
     qmax = nanmaxf(qmax, lnpred);
     qmin = nanminf(qmin, lnpred);
     pmax = nanmaxf(pmax, lnpost);
@@ -178,12 +179,13 @@ struct Fold {
   // Whole tile inside the open chain (the common case): no per-row range tests, one rescale of
   // the running sum per thread and tile, predicated (branch-free) accumulation.
   template <int R>
-  __device__ __forceinline__ void fold_full(const float (&lnpred)[R], const float (&lnpost)[R]) {
+  __device__ __forceinline__ void fold_full(const float (&lnpred)[R], const float (&lnpost)[R],
+                                            const float* diff = nullptr) {
     float a[R];
     float lmax = -CUDART_INF_F;
 #pragma unroll
     for (int q = 0; q < R; ++q) {
-      a[q] = lnpred[q] - lnpost[q];
+      a[q] = diff ? diff[q] : lnpred[q] - lnpost[q];
       qmax = fmaxf(qmax, lnpred[q]);
       qmin = fminf(qmin, lnpred[q]);
       pmax = fmaxf(pmax, lnpost[q]);
@@ -213,9 +215,9 @@ struct Fold {
   // V = 4, R = 8: two fully coalesced float4 loads per thread).
   template <int R, int V = R>
   __device__ __forceinline__ void tile(long long t0, long long t1, const float (&lnpred)[R],
-                                       const float (&lnpost)[R]) {
+                                       const float (&lnpost)[R], const float* diff = nullptr) {
     if (t1 - t0 == (long long)NT * R && t1 <= cur_end) {
-      fold_full<R>(lnpred, lnpost);
+      fold_full<R>(lnpred, lnpost, diff);
       if (t1 < cur_end) return;
       // the chain ends exactly at the tile boundary
       flush();
@@ -233,7 +235,7 @@ struct Fold {
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         const long long r = r0 + (long long)(q / V) * NT * V + (q % V);
-        if (r >= seg_begin && r < seg_end) sample(lnpred[q], lnpost[q]);
+        if (r >= seg_begin && r < seg_end) sample(lnpred[q], lnpost[q], diff ? diff + q : nullptr);
       }
       if (cur_chain < p.nch && cur_end <= t1) {
         flush();
@@ -302,14 +304,32 @@ __device__ __forceinline__ float ldf(const T* p, long long i) {
 struct Accum {
   int device = 0;
   long long nchains = 0;
-  ChainState* state = nullptr;  // device [nchains]
-  double* globals = nullptr;    // device [G_N] per-call scalars
+  // ONE allocation [nchains x ChainState | G_N per-call scalars] = the packed block that crosses
+  // NVLink (hb_accum_packed_ptr): state and globals point into it
+  double* packed = nullptr;
+  ChainState* state = nullptr;  // = packed
+  double* globals = nullptr;    // = packed + 4 * nchains
   long long* start_dev = nullptr;  // device [nchains+1] scratch for the local offsets
   ChainRec* recs = nullptr;        // device scratch
   size_t recs_cap = 0;
   double* gpart = nullptr;  // device scratch
   size_t gpart_cap = 0;
-  // staging for HOST inputs (pinned + device, double-buffered)
+  bool fresh_call = false;  // next merge_kernel overwrites the per-call scalars instead of folding into them
+  // reset runs on the legacy stream (hb_accum_create has no stream argument): the first use on another
+  // stream waits on this event
+  cudaEvent_t ev_reset = nullptr;
+  bool reset_pending = false;
+  // tensor-path range guard: number of saturated / out-of-range FP16 operand conversions (device counter)
+  unsigned long long* guard = nullptr;
+  // finalize outputs
+  double* fin = nullptr;       // device: hb_result + 4*nchains doubles
+  double* fin_host = nullptr;  // pinned mirror (the 128-byte result travels alone unless arrays are asked for)
+};
+
+// Staging for HOST inputs (pinned + device, double-buffered).  Borrowed per call from a per-device free
+// list (stage_acquire / StageLease), so parked accumulators hold no large buffers.
+struct Stage {
+  int device = 0;
   void* pin[2] = {nullptr, nullptr};
   void* dev[2] = {nullptr, nullptr};
   size_t stage_cap = 0;
@@ -317,8 +337,6 @@ struct Accum {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
-  // finalize outputs
-  double* fin = nullptr;  // device: hb_result + 4*nchains doubles
 };
 
 }  // namespace hb

@@ -1,5 +1,7 @@
 // Host-side internal declarations shared by the translation units of libharmonic_b200.
 #pragma once
+#include <string.h>
+
 #include <thread>
 #include <vector>
 
@@ -8,23 +10,38 @@
 namespace hb {
 
 int require_device(int device);
-int ensure_stage(Accum* acc, size_t bytes_per_slot);
-int ensure_pinned(Accum* acc, size_t bytes_per_slot);
+int ensure_stage(Stage* sg, size_t bytes_per_slot);
+int ensure_pinned(Stage* sg, size_t bytes_per_slot);
 void timing_begin(cudaStream_t st);
 void timing_end(cudaStream_t st);
 
 int ensure_scratch(Accum* acc, long long nch, long long nflushers);
+int order_after_reset(Accum* acc, cudaStream_t st);
+int begin_call(Accum* acc, bool has_rows, cudaStream_t st);
 int launch_merge(Accum* acc, const FoldParams& p, long long chain_lo, long long nflushers,
                  cudaStream_t st);
 int prepare_fold(Accum* acc, const int64_t* start, long long chain_lo, long long chain_hi,
                  long long a, long long b, long long nflushers, long long rows_per_flusher,
                  FoldParams* p, cudaStream_t st);
-int reset_call_scalars(Accum* acc, cudaStream_t st);
 int accumulate_precomputed_device(Accum* acc, const void* lnpred, int pd, const void* lnpost, int ld,
                                   const int64_t* start, long long chain_lo, long long chain_hi,
                                   long long a, long long b, cudaStream_t st);
 
 // ---- host staging helpers --------------------------------------------------------------------
+Stage* stage_acquire(int device);
+void stage_release(Stage* s, cudaStream_t st);
+// borrows a Stage for one host-input call; on every exit path (errors included) the copy stream and the
+// compute stream are drained before the buffers return to the free list
+struct StageLease {
+  Stage* s;
+  cudaStream_t st;
+  StageLease(int device, cudaStream_t st_) : s(stage_acquire(device)), st(st_) {}
+  ~StageLease() { stage_release(s, st); }
+  StageLease(const StageLease&) = delete;
+  StageLease& operator=(const StageLease&) = delete;
+  Stage* get() const { return s; }
+};
+
 inline bool is_pinned_host(const void* p) {
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
@@ -34,19 +51,15 @@ inline bool is_pinned_host(const void* p) {
   return attr.type == cudaMemoryTypeHost;
 }
 
-// rows [r0, r1) of a (n, ld) host matrix -> contiguous float32 (n, ncol), split across host threads
-template <typename T>
-inline void convert_rows(const T* src, long long ld, int ncol, long long r0, long long r1, float* dst,
-                         int nthreads) {
-  auto work = [=](long long a, long long b) {
-    for (long long r = a; r < b; ++r) {
-      const T* s = src + r * ld;
-      float* d = dst + (r - r0) * ncol;
-      for (int c = 0; c < ncol; ++c) d[c] = (float)s[c];
-    }
-  };
+// Host worker threads for the pageable-input staging (std::thread, spawned per chunk: the library keeps
+// no thread pool).  They inherit the caller's CPU affinity, so a rank bound to its GPU's NUMA node
+// (hb_bind_host_to_device_node) converts node-locally.  HB_HOST_THREADS overrides the count.
+int host_threads();
+
+template <typename F>
+inline void parallel_rows(long long r0, long long r1, int nthreads, long long min_rows, F work) {
   const long long n = r1 - r0;
-  if (nthreads <= 1 || n < 4096) {
+  if (nthreads <= 1 || n < min_rows) {
     work(r0, r1);
     return;
   }
@@ -60,9 +73,23 @@ inline void convert_rows(const T* src, long long ld, int ncol, long long r0, lon
   for (auto& t : th) t.join();
 }
 
-inline int host_threads() {
-  int n = (int)std::thread::hardware_concurrency();
-  return n > 16 ? 16 : (n < 1 ? 1 : n);
+// rows [r0, r1) of a (n, ld) host matrix -> contiguous float32 (n, ncol), split across host threads
+template <typename T>
+inline void convert_rows(const T* src, long long ld, int ncol, long long r0, long long r1, float* dst,
+                         int nthreads) {
+  parallel_rows(r0, r1, nthreads, 4096, [=](long long a, long long b) {
+    for (long long r = a; r < b; ++r) {
+      const T* s = src + r * ld;
+      float* d = dst + (r - r0) * ncol;
+      for (int c = 0; c < ncol; ++c) d[c] = (float)s[c];
+    }
+  });
+}
+
+inline void copy_bytes(const char* src, char* dst, size_t bytes, int nthreads) {
+  parallel_rows(0, (long long)bytes, nthreads, 1 << 20, [=](long long a, long long b) {
+    memcpy(dst + a, src + a, (size_t)(b - a));
+  });
 }
 
 // ---- flows -------------------------------------------------------------------------------

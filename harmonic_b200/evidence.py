@@ -34,17 +34,21 @@ class Evidence:
         if not model.is_fitted():
             raise ValueError("Model not fitted.")
 
-        self.running_sum = np.zeros(nchains)
-        self.nsamples_per_chain = np.zeros(nchains)
-        self.nsamples_eff_per_chain = np.zeros(nchains)
-
         self.nchains = nchains
+        # running_sum, nsamples_per_chain, nsamples_eff_per_chain, ln_evidence_inv_per_chain are properties:
+        # after add_chains they stay on the device until first read (only the 128-byte result crosses PCIe
+        # per call)
+        self._pc = {"running_sum": np.zeros(nchains), "nsamples_per_chain": np.zeros(nchains),
+                    "nsamples_eff_per_chain": np.zeros(nchains), "ln_evidence_inv_per_chain": None}
+        self._pc_src = None  # accumulator handle holding newer per-chain arrays than _pc
+        self._mean_nsamples_eff = 0.0
+        self.guard_trips = 0
+
         self.ndim = model.ndim
         self.kurtosis = 0.0
         self.n_eff = 0
 
         self.ln_evidence_inv = 0.0
-        self.ln_evidence_inv_per_chain = None
         self.ln_evidence_inv_var = 0.0
         self.ln_evidence_inv_var_var = 0.0
         self.ln_kurtosis = 0.0
@@ -70,6 +74,22 @@ class Evidence:
         self._acc = None
         self._acc_global = None
         self._partials = None  # (nchains, 4): m, s, n, n_nan of THIS process' contributions
+        self._gather = None    # (send view, recv buffer, key) of the NCCL all-gather, kept across calls
+
+    # ------------------------------------------------------------------ lazily fetched per-chain arrays
+    def _fetch_per_chain(self):
+        src = self._pc_src
+        if src is None:
+            return
+        self._pc_src = None
+        arrs = [np.empty(self.nchains, dtype=np.float64) for _ in range(4)]
+        _lib.check(_lib.load().hb_finalize_arrays(src, *[a.ctypes.data for a in arrs], self._stream()))
+        for k, a in zip(("ln_evidence_inv_per_chain", "running_sum", "nsamples_per_chain",
+                         "nsamples_eff_per_chain"), arrs):
+            self._pc[k] = a
+
+    def _stream(self):
+        return _current_stream(self.device)
 
     # ------------------------------------------------------------------ harmonic/evidence.py:100-123
     def set_shift(self, shift_value: float):
@@ -89,10 +109,12 @@ class Evidence:
             self._acc = h
             if self._partials is not None:  # restored from a checkpoint
                 p = np.ascontiguousarray(self._partials, dtype=np.float64)
-                _lib.check(lib.hb_accum_merge(h, p.ctypes.data, None))
+                _lib.check(lib.hb_accum_merge(h, p.ctypes.data, None, self._stream()))
         return self._acc
 
     def _release(self):
+        self._pc_src = None
+        self._gather = None
         for name in ("_acc", "_acc_global"):
             h = getattr(self, name, None)
             if h is not None:
@@ -110,15 +132,18 @@ class Evidence:
         pickled, and what crosses NVLink in the multi-GPU all-gather."""
         if self._acc is not None:
             part = np.empty((self.nchains, 4), dtype=np.float64)
-            _lib.check(_lib.load().hb_accum_export(self._acc, part.ctypes.data, None))
+            _lib.check(_lib.load().hb_accum_export(self._acc, part.ctypes.data, None, self._stream()))
             self._partials = part
         return self._partials
 
     def __getstate__(self):
         self.partials()  # pull the device-side streaming state into the picklable image
+        self._fetch_per_chain()
         st = dict(self.__dict__)
         st["_acc"] = None
         st["_acc_global"] = None
+        st["_gather"] = None
+        st["_pc_src"] = None
         return st
 
     # ------------------------------------------------------------------ harmonic/evidence.py:125-189
@@ -134,6 +159,7 @@ class Evidence:
                                              float(self.shift_value), _lib.C.byref(res), per.ctypes.data))
         self._take(res)
         self.ln_evidence_inv_per_chain = per
+        self._mean_nsamples_eff = float(np.mean(self.nsamples_eff_per_chain))
 
     def _take(self, res):
         self.ln_evidence_inv = res.ln_evidence_inv
@@ -144,6 +170,19 @@ class Evidence:
         self.n_eff = res.n_eff
 
     # ------------------------------------------------------------------ harmonic/evidence.py:215-358
+    def _shard_start(self, start_indices, nloc, sharded, chain_offset):
+        """Global start_indices array (nchains + 1, int64) with this shard's offsets in place [lo, hi]."""
+        lo = int(chain_offset) if sharded else 0
+        hi = lo + nloc
+        loc = start_indices if isinstance(start_indices, np.ndarray) and start_indices.dtype == np.int64 \
+            else np.asarray(start_indices, dtype=np.int64)
+        if lo == 0 and hi == self.nchains:
+            return np.ascontiguousarray(loc), lo, hi
+        start = np.zeros(self.nchains + 1, dtype=np.int64)
+        start[lo:hi + 1] = loc
+        start[hi + 1:] = start[hi]
+        return start, lo, hi
+
     def add_chains(self, chains, num_slices=None, chain_offset=0, comm=None):
         """Add chains and update the inverse-evidence statistics.
 
@@ -154,6 +193,10 @@ class Evidence:
         ``add_chains(local_chains, chain_offset=first_chain_of_this_rank, comm=group_or_True)`` with
         only ITS chains; per-chain partials are all-gathered (torch.distributed) and every rank ends
         with identical statistics.
+
+        Everything the call launches -- flow + fold kernel(s), merge, (all-gather, merge of the gathered
+        blocks,) finalise -- is ordered on ONE CUDA stream (torch's current stream when torch is in use);
+        the call ends with a single stream synchronisation that brings back the 128-byte result.
         """
         sharded = comm is not None and comm is not False
         if sharded:
@@ -172,13 +215,9 @@ class Evidence:
 
         lib = _lib.require_gpu()
         acc = self._get_acc()
-        lo = int(chain_offset) if sharded else 0
-        hi = lo + chains.nchains
-        # global start_indices array with this shard's offsets in place [lo, hi]
-        start = np.zeros(self.nchains + 1, dtype=np.int64)
-        start[lo:hi + 1] = np.asarray(chains.start_indices, dtype=np.int64)
-        start[hi + 1:] = start[hi]
-        stream = None
+        start_loc = chains.start_array() if hasattr(chains, "start_array") else chains.start_indices
+        start, lo, hi = self._shard_start(start_loc, chains.nchains, sharded, chain_offset)
+        stream = self._stream()
 
         if self.batch_calculation:
             if hasattr(self.model, "_check_temperature"):
@@ -187,25 +226,24 @@ class Evidence:
             yr = _lib.ArrayRef(Y)
             if xr.mem != yr.mem:
                 raise ValueError("samples and ln_posterior must live in the same memory space")
-            if xr.mem == _lib.HB_MEM_DEVICE:
-                stream = _current_stream(xr.device if xr.device is not None else self.device)
             h = self.model._get_handle(self.device)
             _lib.check(lib.hb_accumulate_flow(
                 acc, h, float(self.model.temperature), xr.ptr, xr.dtype, xr.ld, yr.ptr, yr.dtype, xr.mem,
                 start.ctypes.data, lo, hi, None, _lib.HB_ACC_NEW_CALL, stream))
         else:
             # user-supplied model without a flow: per-sample predict on the host
-            # (harmonic/evidence.py:285-303), then the accumulation-only kernel
-            Xh, Yh = np.asarray(X), np.asarray(Y, dtype=np.float64)
+            # (harmonic/evidence.py:285-303), then the accumulation-only kernel; float64 travels as float64
+            # and lnpred - ln_posterior is formed in double on the device, as numpy does there
+            Xh, Yh = np.asarray(X), np.ascontiguousarray(Y, dtype=np.float64)
             lnpred = np.empty(Xh.shape[0], dtype=np.float64)
             for i in range(Xh.shape[0]):
                 lnpred[i] = self.model.predict(Xh[i, :])
             lnpred[np.isinf(lnpred)] = np.nan
             _lib.check(lib.hb_accumulate_precomputed(
                 acc, lnpred.ctypes.data, _lib.HB_F64, Yh.ctypes.data, _lib.HB_F64, _lib.HB_MEM_HOST,
-                start.ctypes.data, lo, hi, _lib.HB_ACC_NEW_CALL, None))
+                start.ctypes.data, lo, hi, _lib.HB_ACC_NEW_CALL, stream))
 
-        self._finish_call(lib, acc, comm if sharded else None)
+        self._finish_call(lib, acc, comm if sharded else None, stream)
         self.chains_added = True
         self.check_basic_diagnostic()
 
@@ -216,85 +254,90 @@ class Evidence:
         acc = self._get_acc()
         sharded = comm is not None and comm is not False
         nloc = len(start_indices) - 1
-        lo = int(chain_offset) if sharded else 0
-        hi = lo + nloc
-        if hi > self.nchains or (not sharded and nloc != self.nchains):
+        if chain_offset < 0 or chain_offset + nloc > self.nchains or (not sharded and nloc != self.nchains):
             raise ValueError("nchains do not match")
-        start = np.zeros(self.nchains + 1, dtype=np.int64)
-        start[lo:hi + 1] = np.asarray(start_indices, dtype=np.int64)
-        start[hi + 1:] = start[hi]
+        start, lo, hi = self._shard_start(start_indices, nloc, sharded, chain_offset)
         pr, yr = _lib.ArrayRef(lnpred), _lib.ArrayRef(ln_posterior)
         if pr.mem != yr.mem:
             raise ValueError("lnpred and ln_posterior must live in the same memory space")
-        stream = _current_stream(pr.device if pr.device is not None else self.device) \
-            if pr.mem == _lib.HB_MEM_DEVICE else None
+        stream = self._stream()
         _lib.check(lib.hb_accumulate_precomputed(
             acc, pr.ptr, pr.dtype, yr.ptr, yr.dtype, pr.mem, start.ctypes.data, lo, hi,
             _lib.HB_ACC_NEW_CALL, stream))
-        self._finish_call(lib, acc, comm if sharded else None)
+        self._finish_call(lib, acc, comm if sharded else None, stream)
         self.chains_added = True
         self.check_basic_diagnostic()
 
-    def _finish_call(self, lib, acc, comm):
+    def _finish_call(self, lib, acc, comm, stream):
         fin = acc
         if comm is not None:
             # the one collective of the path: all-gather of [4*nchains partials | 8 scalars] per rank,
-            # device to device over NCCL (host staging only for CPU backends), then one merge kernel
+            # device to device over NCCL (host staging only for CPU backends), then one merge kernel that
+            # REPLACES the state of the gather target -- all on `stream`, no host synchronisation
             if self._acc_global is None:
                 h = _lib.C.c_void_p()
                 _lib.check(lib.hb_accum_create(self.nchains, self.device, _lib.C.byref(h)))
                 self._acc_global = h
             fin = self._acc_global
-            _lib.check(lib.hb_accum_reset(fin))
             n = 4 * self.nchains + 8
-            import torch
             import torch.distributed as dist
             group = None if comm is True else comm
             world = dist.get_world_size(group)
             if dist.get_backend(group) == "nccl":
-                dev = torch.device("cuda", self.device)
-                stream = torch.cuda.current_stream(dev).cuda_stream
-                send = torch.empty(n, dtype=torch.float64, device=dev)
-                _lib.check(lib.hb_stream_sync(None))  # accumulate launches ran on the legacy stream
-                _lib.check(lib.hb_accum_pack(acc, send.data_ptr(), _lib.HB_MEM_DEVICE, stream))
-                recv = torch.empty(world * n, dtype=torch.float64, device=dev)
+                send, recv = self._gather_buffers(lib, acc, n, world)
                 dist.all_gather_into_tensor(recv, send, group=group)
-                _lib.check(lib.hb_accum_merge_packed(fin, world, recv.data_ptr(), n, _lib.HB_MEM_DEVICE, stream))
-                torch.cuda.current_stream(dev).synchronize()
+                _lib.check(lib.hb_accum_merge_packed(fin, world, recv.data_ptr(), n, _lib.HB_MEM_DEVICE,
+                                                     _lib.HB_MERGE_OVERWRITE, stream))
             else:
                 send = np.empty(n, dtype=np.float64)
-                _lib.check(lib.hb_accum_pack(acc, send.ctypes.data, _lib.HB_MEM_HOST, None))
+                _lib.check(lib.hb_accum_pack(acc, send.ctypes.data, _lib.HB_MEM_HOST, stream))
                 recv = np.ascontiguousarray(_allgather(send, comm))
-                _lib.check(lib.hb_accum_merge_packed(fin, world, recv.ctypes.data, n, _lib.HB_MEM_HOST, None))
+                _lib.check(lib.hb_accum_merge_packed(fin, world, recv.ctypes.data, n, _lib.HB_MEM_HOST,
+                                                     _lib.HB_MERGE_OVERWRITE, stream))
         res = _lib.Result()
-        per = np.empty(self.nchains, dtype=np.float64)
-        rsum = np.empty(self.nchains, dtype=np.float64)
-        npc = np.empty(self.nchains, dtype=np.float64)
-        neff = np.empty(self.nchains, dtype=np.float64)
         shift_in = float(self.shift_value) if self.shift_set else float("nan")
-        _lib.check(lib.hb_finalize(fin, self.shift.value, shift_in, _lib.C.byref(res), per.ctypes.data,
-                                   rsum.ctypes.data, npc.ctypes.data, neff.ctypes.data))
+        # finalise on the same stream; only the 128-byte result crosses PCIe, the per-chain arrays stay on
+        # the device until somebody reads them (_fetch_per_chain)
+        _lib.check(lib.hb_finalize(fin, self.shift.value, shift_in, _lib.C.byref(res), None, None, None, None,
+                                   stream))
+        self._pc_src = fin
         if not self.shift_set:
             self.set_shift(res.shift_value)
         self._take(res)
-        self.ln_evidence_inv_per_chain = per
-        self.running_sum = rsum
-        self.nsamples_per_chain = npc
-        self.nsamples_eff_per_chain = neff
+        self._mean_nsamples_eff = res.mean_nsamples_eff
         self.lnargmax, self.lnargmin = res.lnargmax, res.lnargmin
         self.lnprobmax, self.lnprobmin = res.lnprobmax, res.lnprobmin
         self.lnpredictmax, self.lnpredictmin = res.lnpredictmax, res.lnpredictmin
+        trips = int(res.guard_trips)
+        if trips > self.guard_trips:
+            lg.warning_log(
+                "RealNVP tensor-core path: {} launch(es) had inputs outside its guaranteed-accuracy range and "
+                "were re-evaluated on the CUDA cores (float32 FMA arithmetic).".format(trips - self.guard_trips))
+        self.guard_trips = trips
+
+    def _gather_buffers(self, lib, acc, n, world):
+        """Send view on the accumulator's packed device block (zero copy) and a persistent receive buffer."""
+        import torch
+        ptr = _lib.C.c_void_p()
+        _lib.check(lib.hb_accum_packed_ptr(acc, _lib.C.byref(ptr), None))
+        key = (ptr.value, n, world, self.device)
+        if self._gather is None or self._gather[0] != key:
+            dev = torch.device("cuda", self.device)
+            send = torch.as_tensor(_DevView(ptr.value, n), device=dev)
+            recv = _recv_buffer(n * world, dev)
+            self._gather = (key, send, recv)
+        return self._gather[1], self._gather[2]
 
     # ------------------------------------------------------------------ harmonic/evidence.py:360-399
     def check_basic_diagnostic(self):
         NSAMPLES_EFF_WARNING_LEVEL = 30
         LNARG_WARNING_LEVEL = 1000.0
         tests_pass = True
-        if np.mean(self.nsamples_eff_per_chain) <= NSAMPLES_EFF_WARNING_LEVEL:
+        mean_eff = self._mean_nsamples_eff if self._pc_src is not None else np.mean(self.nsamples_eff_per_chain)
+        if mean_eff <= NSAMPLES_EFF_WARNING_LEVEL:
             lg.warning_log(
                 "Evidence may not be accurate due to low number of effective samples (mean number of "
-                "effective samples per chain is {}). Use more samples.".format(
-                    np.mean(self.nsamples_eff_per_chain)))
+                "effective samples per chain is {}). Use more samples.".format(mean_eff))
             tests_pass = False
         if (self.lnargmax - self.lnargmin) >= LNARG_WARNING_LEVEL:
             lg.warning_log(
@@ -348,9 +391,52 @@ class Evidence:
             return cloudpickle.load(fh)
 
 
+def _per_chain_property(name):
+    def get(self):
+        self._fetch_per_chain()
+        return self._pc[name]
+
+    def set_(self, value):
+        self._fetch_per_chain()
+        self._pc[name] = value
+
+    return property(get, set_)
+
+
+for _name in ("running_sum", "nsamples_per_chain", "nsamples_eff_per_chain", "ln_evidence_inv_per_chain"):
+    setattr(Evidence, _name, _per_chain_property(_name))
+
+
+class _DevView:
+    """``n`` float64 values at a raw device pointer, importable by torch.as_tensor without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+_RECV = {}
+
+
+def _recv_buffer(n, dev):
+    """Receive buffers of the all-gather are shared by all Evidence objects of the process (one per size)."""
+    import torch
+    key = (n, dev.index)
+    buf = _RECV.get(key)
+    if buf is None:
+        if len(_RECV) > 8:
+            _RECV.clear()
+        buf = _RECV[key] = torch.empty(n, dtype=torch.float64, device=dev)
+    return buf
+
+
 def _current_stream(device):
+    """torch's current stream on ``device`` when the process uses torch, else the legacy default stream."""
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is None:
+        return None
     try:
-        import torch
         return torch.cuda.current_stream(device).cuda_stream
     except Exception:
         return None

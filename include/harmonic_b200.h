@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define HB_VERSION 100 /* 0.1.0 */
+#define HB_VERSION 200 /* 0.2.0 */
 
 typedef enum {
   HB_OK = 0,
@@ -52,6 +52,8 @@ enum { HB_MEAN_SHIFT = 1, HB_MAX_SHIFT = 2, HB_MIN_SHIFT = 3, HB_ABS_MAX_SHIFT =
 enum { HB_PATH_AUTO = 0, HB_PATH_SIMT = 1, HB_PATH_TCGEN05 = 2, HB_PATH_SIMT_GENERIC = 3 /* no small-ndim register path */ };
 /* flags for hb_accumulate_* */
 enum { HB_ACC_NEW_CALL = 1 /* first launch of an add_chains call: reset the per-call scalars */ };
+/* flags for hb_accum_merge_packed */
+enum { HB_MERGE_OVERWRITE = 1 /* the merged blocks REPLACE the accumulator's state (no separate reset) */ };
 
 #define HB_MAX_HIDDEN 8
 
@@ -97,7 +99,9 @@ typedef struct {
   double lnprobmax, lnprobmin;       /* harmonic/evidence.py:349-350 */
   double lnpredictmax, lnpredictmin; /* harmonic/evidence.py:351-352 */
   double nsamples_total;
-  double reserved[3];
+  double mean_nsamples_eff; /* mean over chains of nsamples_eff_per_chain (harmonic/evidence.py:372-378) */
+  double guard_trips;       /* tensor-path range guard: launches re-run on the CUDA cores since the last reset */
+  double reserved;
 } hb_result;
 
 int hb_version(void);
@@ -133,9 +137,13 @@ int hb_flow_sample(hb_flow* flow, float temperature, const void* eps, int eps_dt
 /* Streaming per-chain state of Evidence (harmonic/evidence.py:65-67,83-85): for every chain the
  * max-rescaled pair (m, s) with ln sum_i exp(lnarg_i) = m + ln s, the sample count n and the NaN
  * count; plus the per-call scalars. */
+/* hb_accum_create resets on the legacy default stream; later calls on any stream order themselves behind
+ * that reset.  hb_accum_destroy parks the accumulator (O(nchains) bytes) for reuse by the next create with
+ * the same (device, nchains); hb_pool_trim frees everything parked, staging buffers included. */
 int hb_accum_create(int64_t nchains, int device, hb_accum** out);
 int hb_accum_destroy(hb_accum* acc);
-int hb_accum_reset(hb_accum* acc);
+int hb_accum_reset(hb_accum* acc, void* stream);
+int hb_pool_trim(void);
 
 /* Replaces the batched branch of Evidence.add_chains (harmonic/evidence.py:260-283,321-352) fused
  * with FlowModel.predict: for chains [chain_lo, chain_hi) evaluate ln phi, form
@@ -157,29 +165,36 @@ int hb_accumulate_precomputed(hb_accum* acc, const void* lnpred, int lnpred_dtyp
 
 /* partials: nchains x 4 doubles (m, s, n, n_nan); globals: 8 doubles
  * (sum lnarg, #finite, lnarg max, lnarg min, lnprob max, lnprob min, lnpred max, lnpred min).
- * Export synchronises.  Merge folds another rank's / an earlier checkpoint's partials in; this is
- * what crosses NVLink (one all-gather of O(nchains) doubles) and what gets pickled. */
-int hb_accum_export(hb_accum* acc, double* partials, double* globals);
-int hb_accum_merge(hb_accum* acc, const double* partials, const double* globals);
+ * Both run on `stream` and synchronise it.  Merge folds another rank's / an earlier checkpoint's partials
+ * in; this is what crosses NVLink (one all-gather of O(nchains) doubles) and what gets pickled. */
+int hb_accum_export(hb_accum* acc, double* partials, double* globals, void* stream);
+int hb_accum_merge(hb_accum* acc, const double* partials, const double* globals, void* stream);
 
 /* Packed form for the multi-GPU exchange: [nchains x 4 partials | 8 globals] = 4*nchains + 8 doubles.
  * hb_accum_pack writes this rank's block to `dst` (HOST or DEVICE; device copies are asynchronous on
- * `stream`): it is the send buffer of the one all-gather of the path.  hb_accum_merge_packed folds
- * `nranks` such blocks (block r at packed + r*stride doubles, rank order = merge order) in one
- * kernel launch. */
+ * `stream`).  The accumulator keeps its state in exactly this layout in ONE device allocation, so
+ * hb_accum_packed_ptr hands out the send buffer of the path's one all-gather without a copy (valid until
+ * the accumulator is destroyed; contents are stream-ordered behind the accumulate calls).
+ * hb_accum_merge_packed folds `nranks` such blocks (block r at packed + r*stride doubles, rank order =
+ * merge order) in one kernel launch; HB_MERGE_OVERWRITE makes them replace the previous state. */
 int hb_accum_pack(hb_accum* acc, double* dst, int mem, void* stream);
+int hb_accum_packed_ptr(hb_accum* acc, double** device_ptr, int64_t* n_doubles);
 int hb_accum_merge_packed(hb_accum* acc, int nranks, const double* packed, int64_t stride, int mem,
-                          void* stream);
+                          int flags, void* stream);
 
 /* Replaces Evidence.process_run (harmonic/evidence.py:125-189) and the shift selection
  * (harmonic/evidence.py:307-319): a single-CTA float64 kernel.  `shift_value_in` is the frozen
  * shift of an earlier call, or NaN to derive it from this call's scalars with `shift_mode`.
  * Optional outputs (HOST, nchains doubles each, may be NULL): ln_evidence_inv_per_chain,
  * running_sum (= exp(m + ln s + shift)), nsamples_per_chain, nsamples_eff_per_chain.
- * Synchronises. */
+ * Runs on `stream` behind the accumulate / merge launches issued there (no device-wide synchronisation),
+ * copies the 128-byte result (plus the arrays when asked for) and synchronises `stream`.
+ * hb_finalize_arrays fetches the per-chain arrays of the most recent hb_finalize later. */
 int hb_finalize(hb_accum* acc, int shift_mode, double shift_value_in, hb_result* out,
                 double* ln_inv_per_chain, double* running_sum, double* nsamples_per_chain,
-                double* nsamples_eff_per_chain);
+                double* nsamples_eff_per_chain, void* stream);
+int hb_finalize_arrays(hb_accum* acc, double* ln_inv_per_chain, double* running_sum,
+                       double* nsamples_per_chain, double* nsamples_eff_per_chain, void* stream);
 
 /* Evidence.process_run (harmonic/evidence.py:125-189) on caller-supplied real-space running totals
  * (HOST arrays of nchains doubles): what the reference computes when process_run() is invoked on
@@ -202,10 +217,18 @@ int hb_stream_sync(void* stream);
 /* timing aid: number of kernels launched by this library in the calling process so far */
 int64_t hb_launch_count(void);
 /* duration (ms, CUDA events on the call's stream) of the flow/accumulate kernel of the most
- * recent hb_accumulate_* / hb_flow_predict call on `acc`/`flow`'s device; for bench.py's
- * roofline block.  Enabled by hb_set_kernel_timing(1). */
+ * recent hb_accumulate_* / hb_flow_predict call on `device`; for bench.py's roofline block.
+ * Enabled by hb_set_kernel_timing(1); the state is per device and mutex-guarded. */
 int hb_set_kernel_timing(int on);
-double hb_last_kernel_ms(void);
+double hb_last_kernel_ms(int device);
+
+/* Host-side helpers for the staged (HOST buffer) path.  Pageable inputs are converted to float32 by up to 16
+ * std::threads per chunk (HB_HOST_THREADS overrides; they inherit the caller's CPU affinity).
+ * hb_bind_host_to_device_node pins the calling thread to the CPUs of the GPU's NUMA node (returns the CPU
+ * count, 0 if the topology is not exposed): call it once per rank before allocating host buffers.
+ * hb_host_copy_gbs: STREAM-style copy rate of the host with `threads` workers (GB/s, read + write). */
+int hb_bind_host_to_device_node(int device);
+double hb_host_copy_gbs(size_t bytes, int threads);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

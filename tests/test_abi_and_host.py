@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_lib.SIGNATURES) == names  # ctypes table mirrors the header one to one
-    assert lib.hb_version() == 100
+    assert lib.hb_version() == 200
 
 
 def test_struct_layouts_match_header():
