@@ -262,7 +262,8 @@ __global__ void merge_partials_kernel(ChainState* __restrict__ state, double* __
 //   ln var = lnV - ln(n_eff-1);  ln varvar = 2 lnV - 3 ln n_eff + ln((K-1) + 2/(n_eff-1))  (:179-187)
 // Single CTA; out layout: hb_result, then 4 arrays of nchains doubles.
 // ------------------------------------------------------------------------------------------
-constexpr int FIN_THREADS = 256;
+constexpr int FIN_THREADS = 1024;
+constexpr int FIN_WARPS = FIN_THREADS / 32;
 
 __device__ double block_max(double v, double* sh) {
 #pragma unroll
@@ -271,7 +272,7 @@ __device__ double block_max(double v, double* sh) {
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
   double r = sh[0];
-  for (int w = 1; w < FIN_THREADS / 32; ++w) r = fmax(r, sh[w]);
+  for (int w = 1; w < FIN_WARPS; ++w) r = fmax(r, sh[w]);
   return r;
 }
 __device__ double block_sum(double v, double* sh) {
@@ -281,10 +282,11 @@ __device__ double block_sum(double v, double* sh) {
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
   double r = 0.0;
-  for (int w = 0; w < FIN_THREADS / 32; ++w) r += sh[w];
+  for (int w = 0; w < FIN_WARPS; ++w) r += sh[w];
   return r;
 }
-// NaN-propagating logsumexp of f(c) over chains (scipy.special.logsumexp semantics)
+// NaN-propagating logsumexp of f(c) over chains (scipy.special.logsumexp semantics); f must be cheap (it is
+// evaluated twice per chain: the callers read values stored by an earlier pass)
 template <typename F>
 __device__ double block_lse(long long n, F f, double* sh) {
   double mx = -CUDART_INF;
@@ -304,11 +306,13 @@ __device__ double block_lse(long long n, F f, double* sh) {
   return mx + log(sum);
 }
 
+// One CTA of 1024 threads.  The four per-chain output arrays double as scratch so that every logarithm /
+// exponential of a chain is evaluated once (float64 transcendentals are what this kernel costs: 1e4 chains took
+// 236 us with 256 threads and per-use recomputation, see profiles/README.md).
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(const ChainState* __restrict__ state, const double* __restrict__ globals,
-                long long nch, int shift_mode, double shift_in, const unsigned long long* __restrict__ guard,
-                double* __restrict__ out) {
-  __shared__ double sh[FIN_THREADS / 32];
+                long long nch, int shift_mode, double shift_in, double* __restrict__ out) {
+  __shared__ double sh[FIN_WARPS];
   hb_result* res = reinterpret_cast<hb_result*>(out);
   double* ln_inv_pc = out + sizeof(hb_result) / sizeof(double);
   double* rsum = ln_inv_pc + nch;
@@ -325,37 +329,36 @@ finalize_kernel(const ChainState* __restrict__ state, const double* __restrict__
                                                                      : -globals[G_ARGMIN];
   }
 
+  // pass 1: L_c -> rsum[] (scratch), ln n_c -> neff_pc[] (scratch); totals
   double nsum = 0.0, n2sum = 0.0, nansum = 0.0;
   for (long long c = threadIdx.x; c < nch; c += FIN_THREADS) {
-    const double n = state[c].n;
-    nsum += n;
-    n2sum += n * n;
-    nansum += state[c].nnan;
+    const ChainState st = state[c];
+    nsum += st.n;
+    n2sum += st.n * st.n;
+    nansum += st.nnan;
+    rsum[c] = (st.s > 0.0) ? st.m + log(st.s) : -CUDART_INF;
+    neff_pc[c] = log(st.n);
   }
   const double N = block_sum(nsum, sh);
   const double N2 = block_sum(n2sum, sh);
   const double NNAN = block_sum(nansum, sh);
   const double lnN = log(N);
-  auto L = [&](long long c) {
-    const ChainState st = state[c];
-    return (st.s > 0.0) ? st.m + log(st.s) : -CUDART_INF;
-  };
-  const double ln_rho = block_lse(nch, L, sh) - lnN;
-  auto lnz = [&](long long c) {
-    const double lrc = L(c) - log(state[c].n);
-    if (isinf(ln_rho) && ln_rho < 0) return -CUDART_INF;  // all sums zero
-    return ln_rho + log(fabs(expm1(lrc - ln_rho)));
-  };
-  const double lnV =
-      block_lse(nch, [&](long long c) { return 2.0 * lnz(c) + log(state[c].n); }, sh) - lnN;
+  const double ln_rho = block_lse(nch, [&](long long c) { return rsum[c]; }, sh) - lnN;
+  // pass 2: ln z_c -> ln_inv_pc[] (scratch)
+  const bool all_zero = isinf(ln_rho) && ln_rho < 0;  // all sums zero
+  for (long long c = threadIdx.x; c < nch; c += FIN_THREADS)
+    ln_inv_pc[c] = all_zero ? -CUDART_INF : ln_rho + log(fabs(expm1(rsum[c] - neff_pc[c] - ln_rho)));
+  __syncthreads();
+  const double lnV = block_lse(nch, [&](long long c) { return 2.0 * ln_inv_pc[c] + neff_pc[c]; }, sh) - lnN;
   const double lnK =
-      block_lse(nch, [&](long long c) { return 4.0 * lnz(c) + log(state[c].n); }, sh) - lnN -
-      2.0 * lnV;
+      block_lse(nch, [&](long long c) { return 4.0 * ln_inv_pc[c] + neff_pc[c]; }, sh) - lnN - 2.0 * lnV;
   const double n_eff = N * N / N2;
+  __syncthreads();
+  // pass 3: the public per-chain arrays replace the scratch values
   for (long long c = threadIdx.x; c < nch; c += FIN_THREADS) {
     const ChainState st = state[c];
-    const double Lc = L(c);
-    ln_inv_pc[c] = Lc - log(st.n);
+    const double Lc = rsum[c];
+    ln_inv_pc[c] = Lc - neff_pc[c];
     rsum[c] = exp(Lc + shift);
     npc[c] = st.n;
     neff_pc[c] = st.n - st.nnan;
@@ -378,7 +381,7 @@ finalize_kernel(const ChainState* __restrict__ state, const double* __restrict__
     res->lnpredictmin = globals[G_PREDMIN];
     res->nsamples_total = N;
     res->mean_nsamples_eff = (N - NNAN) / (double)nch;
-    res->guard_trips = guard ? (double)*guard : 0.0;
+    res->guard_trips = 0.0;  // filled in by the host (Accum::guard_trips)
     res->reserved = 0.0;
   }
 }
@@ -463,8 +466,7 @@ int launch_merge(Accum* acc, const FoldParams& p, long long chain_lo, long long 
   const int threads = 256;
   const int blocks = (int)((p.nch + threads - 1) / threads);
   merge_kernel<<<blocks > 0 ? blocks : 1, threads, 0, st>>>(acc->state, acc->globals, p, chain_lo,
-                                                             nflushers, acc->fresh_call ? 1 : 0);
-  acc->fresh_call = false;
+                                                             nflushers, 0);
   count_launch();
   HB_CUDA(cudaGetLastError());
   return HB_OK;
@@ -501,15 +503,11 @@ int prepare_fold(Accum* acc, const int64_t* start, long long chain_lo, long long
   return HB_OK;
 }
 
-// First launch of an add_chains call: the per-call scalars start afresh.  The reset is folded into the
-// call's first merge_kernel (it overwrites instead of folding); a call without rows resets them here.
+// First launch of an add_chains call: the per-call scalars start afresh.
 int begin_call(Accum* acc, bool has_rows, cudaStream_t st) {
+  (void)has_rows;
   int rc = order_after_reset(acc, st);
   if (rc) return rc;
-  if (has_rows) {
-    acc->fresh_call = true;
-    return HB_OK;
-  }
   reset_globals_kernel<<<1, 32, 0, st>>>(acc->globals);
   count_launch();
   HB_CUDA(cudaGetLastError());
@@ -635,7 +633,6 @@ static void accum_free(Accum* acc) {
   cudaFree(acc->recs);
   cudaFree(acc->gpart);
   cudaFree(acc->fin);
-  cudaFree(acc->guard);
   if (acc->fin_host) cudaFreeHost(acc->fin_host);
   if (acc->ev_reset) cudaEventDestroy(acc->ev_reset);
   delete acc;
@@ -647,8 +644,7 @@ static int accum_reset_on(Accum* acc, cudaStream_t st) {
   reset_packed_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(acc->packed, acc->nchains);
   count_launch();
   HB_CUDA(cudaGetLastError());
-  HB_CUDA(cudaMemsetAsync(acc->guard, 0, sizeof(unsigned long long), st));
-  acc->fresh_call = false;
+  acc->guard_trips = 0;
   return HB_OK;
 }
 
@@ -678,7 +674,6 @@ int hb_accum_create(int64_t nchains, int device, hb_accum** out) {
     cudaError_t e = cudaMalloc(&acc->packed, (4 * nchains + G_N) * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&acc->start_dev, (nchains + 1) * sizeof(long long));
     if (e == cudaSuccess) e = cudaMalloc(&acc->fin, sizeof(hb_result) + 4 * nchains * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&acc->guard, sizeof(unsigned long long));
     if (e == cudaSuccess)
       e = cudaHostAlloc(reinterpret_cast<void**>(&acc->fin_host), sizeof(hb_result) + 4 * nchains * sizeof(double),
                         cudaHostAllocDefault);
@@ -924,7 +919,7 @@ int hb_finalize(hb_accum* h, int shift_mode, double shift_value_in, hb_result* o
   if (rc) return rc;
   // stream-ordered behind the accumulate / merge launches of the same stream: no device-wide sync
   finalize_kernel<<<1, FIN_THREADS, 0, st>>>(acc->state, acc->globals, acc->nchains, shift_mode,
-                                             shift_value_in, acc->guard, acc->fin);
+                                             shift_value_in, acc->fin);
   count_launch();
   HB_CUDA(cudaGetLastError());
   const size_t off = sizeof(hb_result) / sizeof(double);
@@ -936,6 +931,7 @@ int hb_finalize(hb_accum* h, int shift_mode, double shift_value_in, hb_result* o
                           cudaMemcpyDeviceToHost, st));
   HB_CUDA(cudaStreamSynchronize(st));
   memcpy(out, acc->fin_host, sizeof(hb_result));
+  out->guard_trips = (double)acc->guard_trips;
   const double* host = acc->fin_host;
   if (ln_inv_per_chain) memcpy(ln_inv_per_chain, host + off, n * sizeof(double));
   if (running_sum) memcpy(running_sum, host + off + n, n * sizeof(double));

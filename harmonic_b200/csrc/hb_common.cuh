@@ -314,13 +314,12 @@ struct Accum {
   size_t recs_cap = 0;
   double* gpart = nullptr;  // device scratch
   size_t gpart_cap = 0;
-  bool fresh_call = false;  // next merge_kernel overwrites the per-call scalars instead of folding into them
   // reset runs on the legacy stream (hb_accum_create has no stream argument): the first use on another
   // stream waits on this event
   cudaEvent_t ev_reset = nullptr;
   bool reset_pending = false;
-  // tensor-path range guard: number of saturated / out-of-range FP16 operand conversions (device counter)
-  unsigned long long* guard = nullptr;
+  // tensor-path range guard: launches of this accumulator re-run on the CUDA cores since the last reset
+  long long guard_trips = 0;
   // finalize outputs
   double* fin = nullptr;       // device: hb_result + 4*nchains doubles
   double* fin_host = nullptr;  // pinned mirror (the 128-byte result travels alone unless arrays are asked for)

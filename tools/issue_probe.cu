@@ -99,6 +99,96 @@ static void run_mma(const char* name, int n, int nw, long long* dout) {
          (double)cyc / (reps * nw), (double)cyc / reps);
 }
 
+
+// (3) Are tcgen05.mma accumulations into ONE accumulator from SEVERAL issuing warps lossless?  A (TMEM) and B (shared
+//     memory) are all ones, so every MMA adds exactly 16 to each of the 128 x N accumulator words; nw warps issue
+//     `reps` MMAs each with the accumulate flag set into the same zeroed columns.  Any lost update shows as a word
+//     that differs from 16 * reps * nw.
+__global__ void __launch_bounds__(256, 1) mma_atomic(int n, int nw, int reps, int trials, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar[8];
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;  // halves 1.0
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base_s;
+  const int w = threadIdx.x >> 5;
+  long long bad = 0;
+  for (int trial = 0; trial < trials; ++trial) {
+    if (w < 4) {  // warps 0-3 own TMEM lanes 32 w .. 32 w + 31: zero D (columns 0..127), ones in A (columns 320..327)
+      const uint32_t lane_base = ((uint32_t)(w * 32)) << 16;
+      for (int c = 0; c < 128; c += 8)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(tb + lane_base + c), "r"(0u) : "memory");
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(tb + lane_base + 320), "r"(0x3C003C00u) : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (w < nw && (threadIdx.x & 31) == 0) {
+      const uint32_t sb = smem_u32(smem);
+      const uint64_t bd = make_desc(sb + 32768, 16 * n, 128);
+      const uint32_t id = idesc_f16(n);
+      for (int r = 0; r < reps; r += 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;}" ::"r"(tb), "r"(tb + 320), "l"(bd), "r"(id) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[w])) : "memory");
+    }
+    // every thread waits for every issuing warp's commit
+    for (int i = 0; i < nw; ++i)
+      asm volatile("{.reg .pred p; WAIT_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1; @!p bra WAIT_%=;}" ::"r"(smem_u32(&bar[i])), "r"((uint32_t)(trial & 1)) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (w < 4) {
+      const uint32_t lane_base = ((uint32_t)(w * 32)) << 16;
+      const float want = 16.0f * (float)reps * (float)nw;
+      for (int c = 0; c < n; c += 8) {
+        uint32_t v[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(tb + lane_base + c) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int k = 0; k < 8; ++k) bad += (__uint_as_float(v[k]) != want) ? 1 : 0;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)bad);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+  }
+}
+
+static void run_atomic(int n, int nw, long long* dout) {
+  const int reps = 256, trials = 64;
+  cudaMemset(dout, 0, 8);
+  cudaFuncSetAttribute(mma_atomic, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  mma_atomic<<<1, 256, 96 * 1024>>>(n, nw, reps, trials, dout);
+  long long bad = -1;
+  cudaError_t e = cudaMemcpy(&bad, dout, sizeof(bad), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    printf("shared accumulator N=%3d warps=%d  CUDA error %s\n", n, nw, cudaGetErrorString(e));
+    return;
+  }
+  printf("shared accumulator   N=%3d issuing warps=%d  %lld wrong words of %d (x %d trials; %d MMAs per warp)\n", n, nw,
+         bad, 128 * n, trials, reps);
+}
+
 // ---- packed FP32 ---------------------------------------------------------------------------
 // MODE 0: scalar fma chains (8 independent accumulators per thread), 1: fma.rn.f32x2 (4 packed accumulators = the
 // same 8 lane-FMAs per step), 2: scalar FMNMX+FMUL (leaky-relu shape), 3: mul.f32x2 + 2 FMNMX
@@ -175,6 +265,8 @@ int main() {
     }
   for (int nw = 1; nw <= 2; ++nw) run_mma<0>("f16 SS (A in smem)", 128, nw, dout);
   for (int nw = 1; nw <= 3; ++nw) run_mma<0>("f16 SS (A in smem)", 64, nw, dout);
+  for (int nw = 1; nw <= 4; ++nw) run_atomic(32, nw, dout);
+  for (int nw = 2; nw <= 4; ++nw) run_atomic(64, nw, dout);
   float* fout;
   cudaMalloc(&fout, 1024 * 4);
   const int th[4] = {128, 256, 512, 1024};
