@@ -139,7 +139,7 @@ static int flow_run(Flow* f, float T, const void* x, int x_dtype, long long ld, 
   const bool tc = (f->path == HB_PATH_TCGEN05) || (f->path == HB_PATH_AUTO && f->tc_ok);
   if (tc)
     return realnvp_tc_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start,
-                          chain_lo, chain_hi, a, b, st);
+                          chain_lo, chain_hi, a, b, f->tc_guard, st);
   return realnvp_simt_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start,
                           chain_lo, chain_hi, a, b, st);
 }

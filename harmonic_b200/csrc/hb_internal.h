@@ -126,6 +126,10 @@ struct Flow {
   void* tc_image = nullptr;
   size_t tc_image_bytes = 0;
   bool tc_ok = false;
+  // range guard of the tensor path (hb_realnvp_tc.cu): device counter of rows beyond the limits since the last
+  // hb_flow_guard_take, and the limits on |standardised input| / |any conditioning input|
+  unsigned long long* tc_guard = nullptr;
+  float tc_guard_raw = 0.f, tc_guard_all = 0.f;
 };
 
 // kernels: evaluate lnphi for rows [0, n) of x; if acc != nullptr also fold with lnpost into acc.
@@ -141,7 +145,7 @@ int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, lon
 int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
                    const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
                    const int64_t* start, long long chain_lo, long long chain_hi, long long a,
-                   long long b, cudaStream_t st);
+                   long long b, unsigned long long* guard, cudaStream_t st);
 // sampling direction: out[r][0..ndim) = flow(eps[r]) for standard-normal draws eps (f32 / f64), generic SIMT kernels
 int flow_sample_run(Flow* f, float T, const void* eps, int eps_dtype, long long ld, long long n, float* out,
                     long long ldo, cudaStream_t st);

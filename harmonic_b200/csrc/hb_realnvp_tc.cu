@@ -4,49 +4,61 @@
 // + harmonic/evidence.py:278-352 for the shapes the tensor path supports (ndim = 64, <= 8 coupling
 // layers; everything else runs on the CUDA-core kernels).
 //
-// Mapping.  One persistent CTA per SM, NT 128-sample tiles in flight (template parameter; 3 by default,
-// HB_TC_TILES=2 selects the two-tile layout for A/B measurements), 128 NT + 32 (NT + 1) threads:
-//   NT epilogue warpgroups : each owns one tile at a time, one sample per thread (TMEM lane = sample).
-//                     NT = 3 (128 registers per thread): the 32 initially transformed features + the 7 that
-//                     can enter, owned by ORIGINAL index; NT = 2: y[64] with a register rotation per layer
-//   producer warp   : streams the pre-split weight image (FP16 blocks, UMMA canonical no-swizzle K-major
-//                     layout, built once on the host) from L2 into an 8-slot ring of 16 KiB chunks with
-//                     cp.async.bulk + mbarrier
-//   NT MMA warps    : tcgen05.mma issuers, one per tile (the first also allocates TMEM); warp-uniform
-//                     straight-line program with blocking mbarrier waits, one elected lane issues
+// Mapping.  One persistent CTA per SM, three 128-sample tiles in flight:
+//   3 epilogue warpgroups : each owns one tile at a time, one sample per thread (TMEM lane = sample).  A thread keeps
+//                     the 32 initially transformed features + the 7 that can enter, owned by ORIGINAL index
+//   producer warp   : streams the pre-split weight image (FP16 blocks, UMMA canonical no-swizzle K-major layout,
+//                     built once on the host) from L2 into a 7-slot ring of 20 KiB chunks with cp.async.bulk + mbarrier
+//   3 MMA warps     : tcgen05.mma issuers, warp W_MMA + t serves tile t (the first also allocates TMEM); warp-uniform
+//                     straight-line program with blocking mbarrier waits, one elected lane issues.  One issuing warp
+//                     sustains one tcgen05.mma per ~49 cycles whatever N <= 64 is, while the tensor pipe itself needs
+//                     N / 2 cycles (profiles/r2_issue_probe.txt)
+//
+// Arithmetic.  leaky_relu(h) = a h + b |h| with a = (1 + 0.01) / 2, b = (1 - 0.01) / 2 (harmonic/flows.py:170
+// LeakyReLU slope 0.01), so with H = x' W0' (x' = conditioning inputs + constant one, W0' = [W0 ; b0]) a coupling MLP is
+//     O = leaky_relu(H) W2 + b2 = x' V + |H| U,     V = a W0' W2 (+ b2 on the constant row),  U = b W2
+// V (40 x 32) is formed once on the host in float64.  The linear term rides in GEMM1 as 32 more output columns
+// (N = 160: [W0' | V]); the epilogue between the GEMMs (E1) is then only |H| and its FP16 split -- no activation,
+// no bias, nothing but conversions -- which is what the kernel's issue slots go to (profiles/r2_alu_probe.txt).
 //
 // Per coupling layer and tile
-//   GEMM1  H[128x128] = [x(0..31) | new(0..6) | 1] . W0'        A, B from shared memory, K = 40
-//   E1     h = leaky_relu(H), compensated FP16 split, in place   eight 16-column chunks, TMEM loads prefetched
-//   GEMM2  O[128xN2] += h[:, quarter] . [Wt|Ws][quarter, :]      A from TMEM, 6 FP16 MMAs per K = 32 quarter
-//   E2     shift / softplus-clip scale epilogue on y1, log-det
+//   GEMM1  [H | O] [128 x 160] = [x(0..31) | new(0..6) | 1] . [W0' | V]     A, B from shared memory, K = 40
+//   E1     |H| -> FP16 pair (hs, hs - |H|), in place of H                    eight 16-column chunks, loads prefetched
+//   GEMM2  O[128 x 32] += |H|[:, quarter] . U[quarter, :]                    A from TMEM, 6 FP16 MMAs per K = 32 quarter
+//   E2     y -= O (shift) or softplus-clip scale epilogue on y, log-det
+// Scaled layers run GEMM1 with V_scale, GEMM2 with U_scale, hand O to the epilogue, then a second pass O = x' V_shift
+// (8 small MMAs) + |H| U_shift over the same operands, which runs under the softplus / reciprocal / log-det arithmetic.
+//
 // Split-precision contractions with FP32 accumulation in TMEM, float32-equivalent products (~2^-22), every MMA
-// kind::f16 (see the comment at H2_SCALE).  An activation a (GEMM1: a standardised input, GEMM2: a hidden unit) is
-// split with compensation, hs = fp16(a * 2^-11), lo = fp16(a - 2^11 hs); a weight as w_hi (11 significant bits) +
-// w_lo; then  a.w ~= hs.(w_hi 2^11) + hs.(w_lo 2^11) + lo.w_hi  -- the SAME hs block feeds two MMAs.  A tcgen05.mma
-// costs max(~45, N/2) cycles whatever its kind (profiles/r1_mma_probe.txt), so the instruction count is the
-// resource and an FP16 MMA covers K = 16 where a TF32 MMA covers K = 8: GEMM1 8 MMAs per layer (2 main + 4
-// correction over x(0..31), 2 over the new columns + bias), GEMM2 6 per K = 32 quarter.
+// kind::f16.  A weight is w_hi (11 significant bits) + w_lo; an activation a is hs = fp16(a s) (round to nearest) and
+// the exact remainder lo = a - hs / s, rounded to fp16:
+//     a w ~= hs (w_hi / s) + hs (w_lo / s) + lo w_hi                          (the lo w_lo term, <= 2^-22, dropped)
+// GEMM1: s = SX = 2^-5 for the conditioning inputs (written once per tile); GEMM2: s = 1, hs = fp16(|H|) straight out
+// of the accumulator and hs - |H| = -lo by ONE mixed-precision subtract (FHADD), against -u_hi.  O accumulates
+// SO = 2^5 times its value (so that u_lo and v_lo are normal halves); E2 removes the factor inside its FMA.
 // What remains against a float32 FMA chain is the tensor cores' truncating accumulator
 // (profiles/r1_tensor_accum_rounding.txt), see DESIGN.md 4.1.
+//
+// Range guard.  hs = fp16(|H|) needs |H| < 65504 and the truncating accumulator costs accuracy where the flow is
+// evaluated far outside its trained range.  Every epilogue thread tracks max |conditioning input| of its rows (the 32
+// raw features and each layer's new column); rows beyond Params::guard_limit are counted into a device counter which
+// the host reads with the results and answers by re-evaluating the call on the CUDA-core path (hb_api / evidence.py).
+// NaN inputs do not trip it: they propagate through the MMAs to a NaN ln phi as in the reference.
 //
 // GEMM1 without re-staging activations.  The flow permutes by one position per layer
 // (harmonic/flows.py:65-66), so layer l conditions on ORIGINAL features l .. l+31: the features below
 // 32 are still the raw (standardised) inputs, and the j < l features 32+j were frozen by layer j's
 // epilogue.  The A operand is therefore written ONCE per tile -- the raw x(0..31) -- plus one new
-// column per layer; each layer's W0 is stored shifted by l rows ("main", K = 32) next to a K = 8
+// column per layer; each layer's [W0' | V] is stored shifted by l rows ("main", K = 32) next to a K = 8
 // "correction" block whose rows multiply the new columns and a constant-one column that carries the
-// bias b0.  The main part of layer l+1 is issued as soon as layer l's last GEMM2 quarter has drained,
+// biases.  The main part of layer l+1 is issued as soon as layer l's epilogue has read O,
 // i.e. it runs under layer l's epilogue; only the 2-MMA correction waits for the new column.
 //
 // GEMM2 is pipelined with E1 at quarter granularity: quarter q's operands replace its own 32 H columns, its
 // GEMM2 step runs while the epilogue computes quarter q + 1 (one mbarrier per quarter: the epilogue may run a
 // whole layer ahead of the MMA warp, never two phases of one barrier).
-// TMEM, P = 128 columns per tile (H, then per 16-column chunk 8 columns of packed lo pairs + 8 of packed hs pairs):
-//   NT = 3: tile t at column 160 t: P | O (32).  Scaled layers run GEMM2 twice over the same h operands: the scale
-//           rows first, then -- once the epilogue has read the pre-activations out of O (OCONS) -- the shift rows
-//           (OFULL2), which so run under the softplus / reciprocal / log-det arithmetic of the epilogue
-//   NT = 2: tile t at column 256 t: P | 64 unused | O (64: one GEMM2 pass, N = 64 on scaled layers).
+// TMEM: tile t at column 160 t: P (128: H, then per 16-column chunk 8 columns of packed -lo pairs + 8 of packed hs
+// pairs) | O (32).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -63,47 +75,56 @@ constexpr int D = 64;
 constexpr int DH = 32;        // d = conditioning width (round(D/2))
 constexpr int U = 32;         // transformed width
 constexpr int TILE = 128;
-constexpr int SLOT_BYTES = 16384;
-constexpr int MAX_TC_LAYERS = 8;  // one K = 8 correction step holds 7 new columns + the bias column
+constexpr int NT = 3;         // tiles (= epilogue warpgroups) in flight per CTA
+constexpr int NSLOTS = 7;
+constexpr int SLOT_BYTES = 20480;
+constexpr int MAX_TC_LAYERS = 8;  // one K = 8 correction step holds 7 new columns + the constant column
 constexpr int KA = 40;            // A operand columns: 32 raw + 7 new + 1 constant
-constexpr int A_HALF = 0;         // (offset of the FP16 block inside a tile's A operand: it is the whole operand)
 constexpr int A_TILE = KA / 4 * 2048;  // FP16 block, 10 chunks of 8 columns: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
+constexpr int N1 = 128 + U;       // GEMM1 output columns: H | O
+constexpr float SX = 0.03125f, SX_INV = 32.0f;  // conditioning inputs travel as hs = fp16(x SX)
+constexpr float SO = 32.0f, SO_INV = 0.03125f;  // O accumulates SO times its value
+constexpr double LEAKY_SLOPE = 0.01;
 
-// Layout for NT tiles (= epilogue warpgroups) in flight per CTA.
-//   NT = 2: TMEM per tile P 128 | 64 unused | O 64; y[64] per thread with a register rotation
-//   NT = 3: TMEM per tile P 128 | O 32 (480 of 512 columns): scaled layers run GEMM2 in TWO N = 32 passes over the
-//           same h operands (scale, then shift, see the kernel); 128 registers per thread, so the
-//           epilogue keeps only the 32 transformed features + the 7 that can enter (owned by ORIGINAL index)
-template <int NT>
-struct L {
-  static constexpr int NSLOTS = 8;
-  static constexpr int THREADS = NT * 128 + 32 * (NT + 1);  // + producer warp + one MMA warp per tile
-  // shared memory carve-up (bytes)
-  static constexpr int SM_RING = 0;
-  static constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;       // per tile: the FP16 A operand (A_TILE)
-  static constexpr int SM_BIAS = SM_A1 + NT * A_TILE;               // b2: MAX_TC_LAYERS * 64 floats
-  static constexpr int SM_PRE = SM_BIAS + MAX_TC_LAYERS * 64 * 4;   // standardisation: inv_amp[D], -offset*inv_amp[D]
-  static constexpr int SM_BAR = SM_PRE + 2 * D * 4;                 // mbarriers
-  static constexpr int SM_MISC = SM_BAR + 512;                      // tmem ptr, fold scratch
-  static constexpr int SM_TOTAL = SM_MISC + 512;
-  // barrier indices (8 bytes each); per-tile barriers are indexed + tile
-  static constexpr int B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = B_A1FULL + NT,
-                       B_A2 = B_HFULL + NT /* [quarter][tile], one phase per layer */, B_OFULL = B_A2 + 4 * NT,
-                       B_OCONS = B_OFULL + NT /* NT = 3: first pass read, O may be overwritten */,
-                       B_OFULL2 = B_OCONS + NT /* NT = 3: second (shift) pass complete */, B_COUNT = B_OFULL2 + NT;
-  static_assert(B_COUNT * 8 <= 512, "barrier block");
-  // TMEM columns (per tile: + TM_TILE * tile)
-  static constexpr uint32_t TM_P = 0, TM_O = NT == 3 ? 128 : 192, TM_TILE = NT == 3 ? 160 : 256;
-};
+// weight image: per layer GA, GB, then GEMM2 chunks (unscaled: two quarters per chunk; scaled: one per chunk + VT)
+constexpr int GA_BYTES = N1 * 64 * 2;          // [160 x 64 K']: K' < 32 hi (meets lo), K' >= 32 lo / SX (meets hs)
+constexpr int GB_MAIN_BYTES = N1 * 32 * 2;     // [160 x 32 K']: hi / SX (meets hs)
+constexpr int GB_CORR_BYTES = N1 * 16 * 2;     // [160 x 16 K'] x 2: [hi ; lo / SX] and [0 ; hi / SX] over [lo new | hs new]
+constexpr int GB_BYTES = GB_MAIN_BYTES + 2 * GB_CORR_BYTES;
+constexpr int Q32_BYTES = 32 * 96 * 2;         // one K = 32 quarter, N2 = 32: K' < 32 -hi, 32..63 lo, 64..95 hi (all x SO)
+constexpr int Q64_BYTES = 64 * 96 * 2;         // scaled layers: rows 0..31 shift, 32..63 scale
+constexpr int VT_BYTES = U * (64 + 32 + 16 + 16) * 2;  // second pass of a scaled layer: the GEMM1 blocks of V_shift, N = 32
+static_assert(GA_BYTES <= SLOT_BYTES && GB_BYTES <= SLOT_BYTES && 2 * Q32_BYTES <= SLOT_BYTES && Q64_BYTES <= SLOT_BYTES, "slot");
+__host__ __device__ __forceinline__ constexpr int layer_chunks(bool scaled) { return scaled ? 7 : 4; }
+__host__ __device__ __forceinline__ constexpr uint32_t chunk_bytes(bool scaled, int j) {
+  return j == 0 ? GA_BYTES : j == 1 ? GB_BYTES : !scaled ? 2 * Q32_BYTES : j < 6 ? Q64_BYTES : VT_BYTES;
+}
+
+constexpr int THREADS = NT * 128 + 32 * (NT + 1);  // + producer warp + one MMA warp per tile
+// shared memory carve-up (bytes)
+constexpr int SM_RING = 0;
+constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;  // per tile: the FP16 A operand (A_TILE)
+constexpr int SM_PRE = SM_A1 + NT * A_TILE;           // standardisation: inv_amp[D], -offset*inv_amp[D]
+constexpr int SM_BAR = SM_PRE + 2 * D * 4;            // mbarriers
+constexpr int SM_MISC = SM_BAR + 512;                 // tmem ptr, fold scratch
+constexpr int SM_TOTAL = SM_MISC + 512;
+// barrier indices (8 bytes each); per-tile barriers are indexed + tile
+constexpr int B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = B_A1FULL + NT,
+              B_A2 = B_HFULL + NT /* [quarter][tile], one phase per layer */, B_OFULL = B_A2 + 4 * NT /* one phase per pass */,
+              B_OCONS = B_OFULL + NT /* O is in the epilogue's registers: one phase per pass */, B_COUNT = B_OCONS + NT;
+static_assert(B_COUNT * 8 <= 512 && NSLOTS <= 8, "barrier block");
+// TMEM columns (per tile: + TM_TILE * tile)
+constexpr uint32_t TM_P = 0, TM_O = 128, TM_TILE = 160;
 
 struct Params {
   const uint8_t* image;   // weight image: chunks of SLOT_BYTES in consumption order
-  const float* bias;      // per layer 64 floats: bt[32], bs[32]
   const float* pre;       // pre_offset[D], pre_amp[D] or nullptr
   int nlayers;
   int nscaled;
-  int chunks_per_batch;
   float T, sum_log_amp;
+  unsigned long long* guard;  // rows beyond guard_limit (device counter), nullptr = not counted
+  float guard_raw;            // largest |standardised input| (accuracy of the truncating accumulator)
+  float guard_all;            // largest |conditioning input|, new columns included (|H| must stay a finite half)
   long long nrows;
   long long rows_per_wg;  // contiguous rows per epilogue warpgroup (multiple of TILE)
   int nbatches;           // tiles per warpgroup
@@ -148,6 +169,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// the producer's wait: its lane would otherwise spend ~8 % of the SM's issue slots polling (profiles/README.md, r1l)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "nanosleep.u32 64;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -168,15 +203,6 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
                : "memory");
 }
 // D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
 __device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t"
@@ -186,6 +212,7 @@ __device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t adesc, uint64_t 
       "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem]
 __device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t"
@@ -195,15 +222,16 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a, uint64_t bdes
       "}\n" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// {upper 16 bits: fp16(hi_elem), lower 16 bits: fp16(lo_elem)}, round to nearest, saturating
+// {upper 16 bits: fp16(hi_elem), lower 16 bits: fp16(lo_elem)}, round to nearest (overflow -> inf: visible, and
+// excluded by the range guard)
 __device__ __forceinline__ uint32_t pack_f16x2(float hi_elem, float lo_elem) {
   uint32_t d;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
   return d;
 }
 __device__ __forceinline__ uint16_t to_f16(float v) {
   uint16_t d;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(d) : "f"(v));
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(d) : "f"(v));
   return d;
 }
 __device__ __forceinline__ float from_f16(uint16_t h) {
@@ -218,20 +246,9 @@ __device__ __forceinline__ float from_f16(uint16_t h) {
       "=r"(v[o + 17]), "=r"(v[o + 18]), "=r"(v[o + 19]), "=r"(v[o + 20]), "=r"(v[o + 21]),            \
       "=r"(v[o + 22]), "=r"(v[o + 23]), "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]),            \
       "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]), "=r"(v[o + 30]), "=r"(v[o + 31])
-#define HB_W32(v, o)                                                                                \
-  "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]),         \
-      "r"(v[o + 6]), "r"(v[o + 7]), "r"(v[o + 8]), "r"(v[o + 9]), "r"(v[o + 10]), "r"(v[o + 11]),   \
-      "r"(v[o + 12]), "r"(v[o + 13]), "r"(v[o + 14]), "r"(v[o + 15]), "r"(v[o + 16]), "r"(v[o + 17]), \
-      "r"(v[o + 18]), "r"(v[o + 19]), "r"(v[o + 20]), "r"(v[o + 21]), "r"(v[o + 22]), "r"(v[o + 23]), \
-      "r"(v[o + 24]), "r"(v[o + 25]), "r"(v[o + 26]), "r"(v[o + 27]), "r"(v[o + 28]), "r"(v[o + 29]), \
-      "r"(v[o + 30]), "r"(v[o + 31])
 #define HB_LIST32                                                                                     \
   "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, " \
   "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}"
-#define HB_LIST32_FROM1                                                                              \
-  "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, " \
-  "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32}"
-
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " HB_LIST32 ", [%32];"
                : HB_R32(v, 0)
@@ -240,10 +257,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], " HB_LIST32_FROM1 ";" ::"r"(taddr), HB_W32(v, 0)
-               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -268,13 +281,6 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
                :
                : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -284,33 +290,15 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// UMMA shared-memory descriptor, K-major, no swizzle: element (r, k) of a [rows x K] tf32 operand
-// lives at (r/8)*SBO + (r%8)*16 + (k/4)*LBO + (k%4)*4 bytes.
+// UMMA shared-memory descriptor, K-major, no swizzle: element (r, k) of a [rows x K] 16-bit operand
+// lives at (r/8)*SBO + (r%8)*16 + (k/8)*LBO + (k%8)*2 bytes.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
          (1ull << 46);
 }
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  // c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
 __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
   // c=F32 (1<<4), a=b=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -387,52 +375,41 @@ __device__ __forceinline__ void load_row<double>(const double* __restrict__ x, l
   }
 }
 
-// Both GEMMs run entirely as kind::f16: one FP16 MMA covers K = 16 at the same ~45-cycle cost as a TF32 MMA
-// covering K = 8 (profiles/r1_mma_probe.txt), and an 11-bit significand is all the main term needs.
-// Compensated split of an activation h (GEMM1: a standardised input x):  hs = fp16(h * 2^-11) (round to nearest),  lo = h - 2^11 * float(hs)  (exact in
-// float32, whatever hs lost to rounding or to the half subnormal range), stored as fp16(lo).  Then
-//   h . w  ~=  hs . (w_hi * 2^11)  +  hs . (w_lo * 2^11)  +  lo . w_hi       (the lo . w_lo term, <= 2^-22, dropped)
-// with all products exact in the tensor core.  hs is a normal half for |h| in [0.125, 1.3e8]; below that lo
-// carries the remainder (|lo| <= 6e-5, absolute error <= 3e-8).  Beyond 1.3e8 the halves saturate.
-constexpr float H2_SCALE = 4.8828125e-4f;  // 2^-11
-constexpr float H2_INV = 2048.0f;
-__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {  // {low half, high half}
-  float2 r;
-  asm("{.reg .b16 a, b; mov.b32 {a, b}, %2; cvt.f32.f16 %0, a; cvt.f32.f16 %1, b;}" : "=f"(r.x), "=f"(r.y) : "r"(v));
-  return r;
+// Split of a pair of conditioning inputs: hs = fp16(v SX) packed, lo = v - hs / SX (exact in float32, one
+// mixed-precision FMA each) packed.  hs is a normal half for |v| in [2^-9, 2.1e6]; below that lo carries the value.
+__device__ __forceinline__ void split_x_pair(float va, float vb, uint32_t& hs, uint32_t& lo) {
+  hs = pack_f16x2(vb * SX, va * SX);
+  float la, lb;
+  const uint16_t m = 0xD000;  // fp16(-SX_INV) = -32
+  asm("{.reg .b16 a, b; mov.b32 {a, b}, %2; fma.rn.f32.f16 %0, a, %5, %3; fma.rn.f32.f16 %1, b, %5, %4;}"
+      : "=f"(la), "=f"(lb)
+      : "r"(hs), "f"(va), "f"(vb), "h"(m));
+  lo = pack_f16x2(lb, la);
 }
 
-// E1 for one 16-column chunk: h = leaky_relu(H) -> wh: 8 words of packed hs pairs, wl: 8 words of packed lo pairs
-// (the compensated split above).  The bias b0 is already inside H (constant-one column of the A operand).
+// E1 for one 16-column chunk of H: wh = 8 words of packed hs = fp16(|H|) pairs, wl = 8 words of packed fp16(hs - |H|)
+// pairs (= -lo, met by -u_hi in the weight image).  Per pair: F2FP, LOP3, 2 FHADD, F2FP.
 __device__ __forceinline__ void e1_chunk(const uint32_t (&v)[16], uint32_t (&wl)[8], uint32_t (&wh)[8]) {
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
-    float h0 = __uint_as_float(v[2 * jj]), h1 = __uint_as_float(v[2 * jj + 1]);
-    h0 = fmaxf(h0, 0.01f * h0);
-    h1 = fmaxf(h1, 0.01f * h1);
-    const uint32_t hs = pack_f16x2(h1 * H2_SCALE, h0 * H2_SCALE);
-    const float2 u = unpack_f16x2(hs);
+    const float h0 = __uint_as_float(v[2 * jj]), h1 = __uint_as_float(v[2 * jj + 1]);
+    const uint32_t hs = pack_f16x2(h1, h0) & 0x7fff7fffu;
+    float n0, n1;
+    asm("{.reg .b16 a, b; mov.b32 {a, b}, %2; sub.rn.f32.f16 %0, a, %3; sub.rn.f32.f16 %1, b, %4;}"
+        : "=f"(n0), "=f"(n1)
+        : "r"(hs), "f"(fabsf(h0)), "f"(fabsf(h1)));
     wh[jj] = hs;
-    wl[jj] = pack_f16x2(fmaf(u.y, -H2_INV, h1), fmaf(u.x, -H2_INV, h0));
+    wl[jj] = pack_f16x2(n1, n0);
   }
 }
 
-__device__ __forceinline__ int layer_chunks(bool scaled) { return scaled ? 7 : 5; }
-
-template <typename XT, typename LT, bool FOLD, int NT>
-__global__ void __launch_bounds__(L<NT>::THREADS, 1)
+template <typename XT, typename LT, bool FOLD>
+__global__ void __launch_bounds__(THREADS, 1)
 realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __restrict__ lnpost,
                   float* __restrict__ lnpred_out, FoldParams fp) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  using C = L<NT>;
-  constexpr int NWG = NT, THREADS = C::THREADS, NSLOTS = C::NSLOTS;
-  constexpr int SM_RING = C::SM_RING, SM_A1 = C::SM_A1, SM_BIAS = C::SM_BIAS, SM_PRE = C::SM_PRE, SM_BAR = C::SM_BAR,
-                SM_MISC = C::SM_MISC;
-  constexpr int B_WFULL = C::B_WFULL, B_WEMPTY = C::B_WEMPTY, B_A1FULL = C::B_A1FULL, B_HFULL = C::B_HFULL,
-                B_A2 = C::B_A2, B_OFULL = C::B_OFULL, B_OCONS = C::B_OCONS, B_OFULL2 = C::B_OFULL2;
-  constexpr uint32_t TM_P = C::TM_P, TM_O = C::TM_O, TM_TILE = C::TM_TILE;
+  constexpr int NWG = NT;
   constexpr int W_PROD = 4 * NT, W_MMA = W_PROD + 1;  // weight producer warp; the MMA warps follow
-  (void)B_OCONS; (void)B_OFULL2;
   // lane-0 broadcast: tells the compiler the warp index (and with it the role dispatch below) is
   // warp-uniform, so the MMA warps' addresses, descriptors and loop state live on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -441,7 +418,6 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   const uint32_t bar0 = sbase + SM_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + SM_MISC);
-  float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS);
   float* pre_s = reinterpret_cast<float*>(smem + SM_PRE);
   const int nl = P.nlayers;
 #ifdef HB_TC_TRACE
@@ -459,7 +435,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOTS; ++i) {
       mbar_init(BAR(B_WFULL + i), 1);
-      mbar_init(BAR(B_WEMPTY + i), NWG);  // both MMA warps release a slot
+      mbar_init(BAR(B_WEMPTY + i), NWG);  // every MMA warp releases a slot
     }
     for (int t = 0; t < NWG; ++t) {
       mbar_init(BAR(B_A1FULL + t), 128);
@@ -467,11 +443,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       for (int q = 0; q < 4; ++q) mbar_init(BAR(B_A2 + NT * q + t), 128);
       mbar_init(BAR(B_OFULL + t), 1);
       mbar_init(BAR(B_OCONS + t), 128);
-      mbar_init(BAR(B_OFULL2 + t), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < nl * 64; i += THREADS) bias_s[i] = P.bias[i];
   for (int i = threadIdx.x; i < D; i += THREADS) {
     const float inv = P.pre ? 1.f / P.pre[D + i] : 1.f;
     pre_s[i] = inv;
@@ -496,13 +470,12 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       for (int b = 0; b < P.nbatches; ++b) {
         const uint8_t* src = P.image;
         for (int l = 0; l < nl; ++l) {
-          const int nc = layer_chunks(l < P.nscaled);
+          const bool scaled = l < P.nscaled;
+          const int nc = layer_chunks(scaled);
           for (int j = 0; j < nc; ++j, ++g) {
-            // only the occupied prefix of a chunk travels: GEMM1 main hs block 8 KiB, [lo | hs] block 16 KiB, the
-            // two new-column blocks 8 KiB, a GEMM2 chunk (one N2 = 64 quarter or two N2 = 32 quarters) 12 KiB
-            const uint32_t bytes = j == 1 ? 16384u : (j < 3 ? 8192u : 12288u);
+            const uint32_t bytes = chunk_bytes(scaled, j);  // only the occupied prefix of a slot travels
             const uint32_t slot = g % NSLOTS, use = g / NSLOTS;
-            mbar_wait(BAR(B_WEMPTY + slot), (use & 1) ^ 1);
+            mbar_wait_relaxed(BAR(B_WEMPTY + slot), (use & 1) ^ 1);
             mbar_expect_tx(BAR(B_WFULL + slot), bytes);
             bulk_g2s(sbase + SM_RING + slot * SLOT_BYTES, src, bytes, BAR(B_WFULL + slot));
             src += SLOT_BYTES;
@@ -511,43 +484,52 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       }
     }
   } else if (warp >= W_MMA) {
-    // ===== MMA issuers: warp 9 serves tile 0, warp 10 tile 1.  Each runs a straight-line program
-    // per layer with blocking mbarrier waits; the whole warp executes it (warp-uniform, so the
-    // descriptors stay in uniform registers) and one elected lane issues.  A weight slot is
-    // released when both warps have committed on it (WEMPTY expects two arrivals).
+    // ===== MMA issuers: warp W_MMA + t serves tile t.  Each runs a straight-line program per layer with blocking
+    // mbarrier waits; the whole warp executes it (warp-uniform, so the descriptors stay in uniform registers) and
+    // one elected lane issues.  A weight slot is released when every MMA warp has committed on it.
     const int t = warp - W_MMA;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
-    const uint32_t ih128 = make_idesc_f16(128), ih64 = make_idesc_f16(64), ih32 = make_idesc_f16(32);
+    const uint32_t ih1 = make_idesc_f16(N1), ih32 = make_idesc_f16(32);
     const uint32_t a_h = sbase + SM_A1 + t * A_TILE;  // FP16 block: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
-    const uint64_t adx_f16 = make_desc(a_h, 2048, 128), adn_f16 = make_desc(a_h + 8 * 2048, 2048, 128);
+    const uint64_t adx = make_desc(a_h, 2048, 128), adn = make_desc(a_h + 8 * 2048, 2048, 128);
     auto wwait = [&](uint32_t gidx) {
       mbar_wait(BAR(B_WFULL + (gidx % NSLOTS)), (gidx / NSLOTS) & 1);
     };
     auto chunk_addr = [&](uint32_t gidx) { return sbase + SM_RING + (gidx % NSLOTS) * SLOT_BYTES; };
-    auto release = [&](uint32_t gidx) {
-      if (elect_one()) tc_commit(BAR(B_WEMPTY + (gidx % NSLOTS)));
-      __syncwarp();
-    };
-    // main part of GEMM1: H = x(0..31) . W0main, three FP16 products on the compensated split of x (as GEMM2).
-    // Chunk g+1 = FP16 [128 x 64 K']: w_hi (meets lo) | w_lo * 2^11 (meets hs); chunk g = FP16 [128 x 32 K']:
-    // w_hi * 2^11 (meets the same hs block); corrections first (small terms), then the main term.
-    auto issue_main = [&](uint32_t g) {
-      wwait(g);
-      wwait(g + 1);
-      tc_fence_after();
-      const uint64_t wt = make_desc(chunk_addr(g), 2048, 128), wh = make_desc(chunk_addr(g + 1), 2048, 128);
+    // x' . B for the K = 32 raw inputs ("main") and the K = 8 new / constant columns ("corr"), B = GEMM1-shaped
+    // blocks of n output rows at ga (the [n x 64 K'] block), gb (the [n x 32 K'] block) and gb + 32 n 2 (corrections).
+    // Small terms first, then the main term.
+    auto issue_main = [&](uint32_t d, uint32_t ga, uint32_t gb, uint32_t n, uint32_t idesc, uint32_t acc0) {
+      const uint64_t wh = make_desc(ga, n * 16, 128), wt = make_desc(gb, n * 16, 128);
+      const uint64_t kstep = (uint64_t)((n * 32) >> 4);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_ss_f16(tb + TM_P, adx_f16 + (uint64_t)(k * 256), wh + (uint64_t)(k * 256), ih128, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) mma_ss_f16(d, adx + (uint64_t)(k * 256), wh + (uint64_t)k * kstep, idesc, k ? 1u : acc0);
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          mma_ss_f16(tb + TM_P, adx_f16 + (uint64_t)((2 + k) * 256), wt + (uint64_t)(k * 256), ih128, 1);
+        for (int k = 0; k < 2; ++k) mma_ss_f16(d, adx + (uint64_t)((2 + k) * 256), wt + (uint64_t)k * kstep, idesc, 1);
       }
       __syncwarp();
     };
-    uint32_t g = 0, it = 0, sc_it = 0;
-    (void)sc_it;
+    auto issue_corr = [&](uint32_t d, uint32_t gc, uint32_t n, uint32_t idesc) {
+      // K' = 16 each over A = [lo new | hs new]: B = [hi ; lo / SX], then B = [0 ; hi / SX]
+      const uint64_t wc = make_desc(gc, n * 16, 128);
+      mma_ss_f16(d, adn, wc, idesc, 1);
+      mma_ss_f16(d, adn, wc + (uint64_t)((n * 32) >> 4), idesc, 1);
+    };
+    // one GEMM2 quarter: 6 MMAs over chunk pair (2 q, 2 q + 1) of P against the quarter block at wbase (row stride lbo2)
+    auto issue_quarter = [&](int q, uint32_t wbase, uint32_t lbo2) {
+      const uint64_t bd = make_desc(wbase, lbo2, 128);
+      const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
+      const uint32_t a0 = tb + TM_P + 32 * q;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t a_lo = a0 + 16 * half, a_hs = a_lo + 8;
+        mma_ts_f16(tb + TM_O, a_lo, bd + (uint64_t)half * kstep2, ih32, 1);
+        mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(2 + half) * kstep2, ih32, 1);
+        mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(4 + half) * kstep2, ih32, 1);
+      }
+    };
+    uint32_t g = 0, it = 0, pit = 0;
     for (int b = 0; b < P.nbatches; ++b) {
       for (int l = 0; l < nl; ++l, ++it) {
         const bool scaled = l < P.nscaled;
@@ -555,264 +537,87 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         // ---- GEMM1: (main, unless issued early) + correction
         mbar_wait(BAR(B_A1FULL + t), par);
         TR(20);
-        if (l == 0) issue_main(g);
-        wwait(g + 2);
+        if (l == 0) {
+          wwait(g);
+          wwait(g + 1);
+          tc_fence_after();
+          issue_main(tb + TM_P, chunk_addr(g), chunk_addr(g + 1), N1, ih1, 0);
+        }
+        wwait(g + 1);
         tc_fence_after();
         {
-          const uint64_t wc = make_desc(chunk_addr(g + 2), 2048, 128);
+          const uint32_t gc = chunk_addr(g + 1) + GB_MAIN_BYTES;
           if (elect_one()) {
-            // K' = 16 each over A = [lo new | hs new]: B = [w_hi ; w_lo * 2^11], then B = [0 ; w_hi * 2^11]
-            mma_ss_f16(tb + TM_P, adn_f16, wc + (uint64_t)(4096 >> 4), ih128, 1);
-            mma_ss_f16(tb + TM_P, adn_f16, wc, ih128, 1);
+            issue_corr(tb + TM_P, gc, N1, ih1);
             tc_commit(BAR(B_HFULL + t));
             tc_commit(BAR(B_WEMPTY + (g % NSLOTS)));
             tc_commit(BAR(B_WEMPTY + ((g + 1) % NSLOTS)));
-            tc_commit(BAR(B_WEMPTY + ((g + 2) % NSLOTS)));
           }
           __syncwarp();
           TR(21);
         }
-        // ---- GEMM2: four K = 32 quarters, each as soon as its half of E1 has landed
-        const uint32_t n2 = scaled ? 64u : 32u;
-        const uint32_t lbo2 = n2 * 16u;
-        const uint32_t qbytes = 12 * lbo2;  // one quarter's weight block: 12 K'-chunks of 8 halves
-        const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
-        // NT = 3: O holds 32 columns, scaled layers take the SCALE rows (32..63 of each quarter block, + 4 row
-        // groups of 128 bytes) in this pass: their epilogue is the long one, the shift pass runs under it
-        const bool two_pass = NT == 3 && scaled;
-        const uint32_t ih2 = (scaled && NT != 3) ? ih64 : ih32;
+        // ---- GEMM2: four K = 32 quarters, each as soon as its part of E1 has landed.  Scaled layers take the SCALE
+        // rows (32..63 of each quarter block: + 4 row groups of 128 bytes) in this pass: their epilogue is the long one
+        const uint32_t lbo2 = scaled ? 64u * 16u : 32u * 16u;
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
-          const uint32_t gw = g + 3 + (scaled ? q : (q >> 1));
-          // (one barrier per quarter: with two phases per layer on one barrier the epilogue, no longer held back by
-          // a Q-buffer hand-back, could complete both before this warp has seen the first)
+          const uint32_t gw = g + 2 + (scaled ? q : (q >> 1));
           mbar_wait(BAR(B_A2 + NT * q + t), par);
           TR(22 + q);
           wwait(gw);
           tc_fence_after();
-          // quarter block in the chunk: FP16 [N2 x 96 K']: K' 0-31 w_hi (meets lo), 32-63 w_lo * 2^11 and
-          // 64-95 w_hi * 2^11 (both meet the scaled hi block).  Chunk c = 2 q + half holds its operands in
-          // place of its 16 H columns: 8 columns of packed lo pairs, 8 of packed scaled hi pairs.
-          const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? qbytes : 0) + (two_pass ? 512u : 0u);
-          const uint64_t bd = make_desc(wbase, lbo2, 128);
-          const uint32_t a0 = tb + TM_P + 32 * q;
+          const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? (uint32_t)Q32_BYTES : 0u) + (scaled ? 512u : 0u);
           if (elect_one()) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint32_t a_lo = a0 + 16 * half, a_hs = a_lo + 8;
-              mma_ts_f16(tb + TM_O, a_lo, bd + (uint64_t)half * kstep2, ih2, (q | half) ? 1u : 0u);
-              mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(2 + half) * kstep2, ih2, 1);
-              mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(4 + half) * kstep2, ih2, 1);
-            }
+            issue_quarter(q, wbase, lbo2);
             if (q == 3) tc_commit(BAR(B_OFULL + t));
-            if (!two_pass && (scaled || (q & 1))) tc_commit(BAR(B_WEMPTY + (gw % NSLOTS)));
+            if (!scaled && (q & 1)) tc_commit(BAR(B_WEMPTY + (gw % NSLOTS)));
           }
           __syncwarp();
           TR(26 + q);
         }
-        if constexpr (NT == 3) {
-          if (scaled) {
-            // ---- second pass: the shift rows (0..31 of each quarter block) over the same h operands, into the
-            // same 32 O columns once the epilogue has read the scale pre-activations out of them
-            mbar_wait(BAR(B_OCONS + t), sc_it & 1);
-            tc_fence_after();
-            TR(32);
+        if (scaled) {
+          // ---- second pass: O = x' V_shift + |H| U_shift (rows 0..31 of each quarter block) once the epilogue has
+          // read the scale pre-activations out of O
+          mbar_wait(BAR(B_OCONS + t), pit & 1);
+          ++pit;
+          wwait(g + 6);
+          tc_fence_after();
+          TR(32);
+          {
+            const uint32_t vt = chunk_addr(g + 6);
+            issue_main(tb + TM_O, vt, vt + U * 64 * 2, U, ih32, 0);
             if (elect_one()) {
+              issue_corr(tb + TM_O, vt + U * 96 * 2, U, ih32);
 #pragma unroll 1
               for (int q = 0; q < 4; ++q) {
-                const uint64_t bd = make_desc(chunk_addr(g + 3 + q), lbo2, 128);
-                const uint32_t a0 = tb + TM_P + 32 * q;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                  const uint32_t a_lo = a0 + 16 * half, a_hs = a_lo + 8;
-                  mma_ts_f16(tb + TM_O, a_lo, bd + (uint64_t)half * kstep2, ih32, (q | half) ? 1u : 0u);
-                  mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(2 + half) * kstep2, ih32, 1);
-                  mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(4 + half) * kstep2, ih32, 1);
-                }
-                tc_commit(BAR(B_WEMPTY + ((g + 3 + q) % NSLOTS)));
+                issue_quarter(q, chunk_addr(g + 2 + q), lbo2);
+                tc_commit(BAR(B_WEMPTY + ((g + 2 + q) % NSLOTS)));
               }
-              tc_commit(BAR(B_OFULL2 + t));
+              tc_commit(BAR(B_OFULL + t));
+              tc_commit(BAR(B_WEMPTY + ((g + 6) % NSLOTS)));
             }
             __syncwarp();
-            TR(33);
           }
+          TR(33);
         }
         g += layer_chunks(scaled);
-        // ---- early main part of the next layer: runs under this layer's E2.  P is GEMM2's A operand
-        // until the last quarter has drained.
+        // ---- O is in the epilogue's registers (and with it every MMA that read P has completed): the main part of
+        // the next layer overwrites P and O under this layer's E2
+        mbar_wait(BAR(B_OCONS + t), pit & 1);
+        ++pit;
+        TR(30);
         if (l + 1 < nl) {
-          if (two_pass) mbar_wait(BAR(B_OFULL2 + t), sc_it & 1);
-          else mbar_wait(BAR(B_OFULL + t), par);
-          TR(30);
-          issue_main(g);
+          wwait(g);
+          wwait(g + 1);
+          tc_fence_after();
+          issue_main(tb + TM_P, chunk_addr(g), chunk_addr(g + 1), N1, ih1, 0);
           TR(31);
         }
-        if (two_pass) ++sc_it;
       }
     }
-  } else if constexpr (NT == 2) {
-    // ===== epilogue warpgroups =====
-    const int wg = warp >> 2;              // 0 / 1
-    const int tid = threadIdx.x & 127;     // TMEM lane == sample row within the tile
-    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    const uint32_t tm_p = tmem_base + lane_base + wg * TM_TILE + TM_P;
-    const uint32_t tm_o = tmem_base + lane_base + wg * TM_TILE + TM_O;
-    uint8_t* a1 = smem + SM_A1 + wg * A_TILE;
-    double* scratch = reinterpret_cast<double*>(smem + SM_MISC + 16) + wg * 12;
-    const int flusher = blockIdx.x * NWG + wg;
-    const long long row_lo = (long long)flusher * P.rows_per_wg;
-    long long row_hi = row_lo + P.rows_per_wg;
-    if (row_hi > P.nrows) row_hi = P.nrows;
-    const bool had_rows = row_lo < P.nrows;
-    // named barriers 1 and 2 are private to the two warpgroups
-    Fold<128> fold(fp, flusher, tid, scratch, (FOLD && had_rows) ? row_lo : 0, 1 + wg);
-    const float invT = 1.f / P.T;
-    const float base_const = -(float)D * logf(P.T) - 0.5f * (float)D * 1.8378770664093453f;
-    uint32_t it = 0;
-
-    for (int b = 0; b < P.nbatches; ++b) {
-      const long long t0 = row_lo + (long long)b * TILE;
-      const long long r = t0 + tid;
-      const bool live = r < row_hi;
-      const long long rr = live ? r : 0;
-      float y[D];
-      TR(1);
-      load_row<XT>(x, ld, rr, y);
-      if (r + TILE < row_hi) {  // pull the next tile's row into L2 while this tile computes
-        const char* nx = reinterpret_cast<const char*>(x + (r + TILE) * ld);
-#pragma unroll
-        for (int q = 0; q < (int)(D * sizeof(XT)); q += 128) prefetch_l2(nx + q);
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
-      // ---- A operand, written once per tile.  TF32 block: hi of raw features 0..31 (K-chunks 0-7),
-      // zeroed new columns and a constant one in column 39 (K-chunks 8, 9).  FP16 block (8 values per
-      // 16-byte chunk): lo of raw 0..31 (chunks 0-3), hi of raw (4-7), lo of new (8), hi of new (9).
-      // (GEMM1 of the previous tile has completed: its HFULL was waited.)
-#pragma unroll
-      for (int c = 0; c < DH / 8; ++c) {
-        uint4 plo, phi;
-        uint32_t* ql = &plo.x;
-        uint32_t* qh = &phi.x;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float va = y[8 * c + 2 * q], vb = y[8 * c + 2 * q + 1];
-          const uint32_t hs = pack_f16x2(vb * H2_SCALE, va * H2_SCALE);
-          const float2 bk = unpack_f16x2(hs);
-          ql[q] = pack_f16x2(fmaf(bk.y, -H2_INV, vb), fmaf(bk.x, -H2_INV, va));
-          qh[q] = hs;
-        }
-        *reinterpret_cast<uint4*>(a1 + A_HALF + c * 2048 + tid * 16) = plo;
-        *reinterpret_cast<uint4*>(a1 + A_HALF + (4 + c) * 2048 + tid * 16) = phi;
-      }
-      {
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(a1 + A_HALF + 8 * 2048 + tid * 16) = z;
-        *reinterpret_cast<uint4*>(a1 + A_HALF + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x10000000u);
-      }
-      float ldj = 0.f;
-      for (int l = 0; l < nl; ++l, ++it) {
-        const uint32_t par = it & 1;
-        const bool scaled = l < P.nscaled;
-        const float* b2 = bias_s + l * 64;
-        fence_proxy_async();
-        tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
-        mbar_arrive(BAR(B_A1FULL + wg));
-        TR(2);
-        // ---- E1 in eight 16-column chunks, software pipelined: chunk c + 1 is in flight from TMEM while
-        // chunk c is computed.  Chunks 2q, 2q + 1 form quarter q: its FP16 operands replace its H columns and
-        // its GEMM2 step runs under the following chunks.
-        mbar_wait(BAR(B_HFULL + wg), par);
-        tc_fence_after();
-        TR(3);
-        {
-          uint32_t va[16], vb[16];
-          tmem_ld16(tm_p, va);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t(&cur)[16] = (c & 1) ? vb : va;
-            uint32_t(&nxt)[16] = (c & 1) ? va : vb;
-            const int q = c >> 1;
-            tmem_ld_wait16(cur);
-            if (c < 7) tmem_ld16(tm_p + (c + 1) * 16, nxt);
-            uint32_t wl[8], wh[8];
-            e1_chunk(cur, wl, wh);
-            tmem_st8(tm_p + c * 16, wl);      // in place of the chunk's own H columns (already in registers)
-            tmem_st8(tm_p + c * 16 + 8, wh);
-            if (c & 1) {
-              tmem_st_wait();
-              tc_fence_before();
-              mbar_arrive(BAR(B_A2 + NT * q + wg));
-              TR(4 + q);
-            }
-          }
-        }
-        // ---- E2: y1 = (y1 - shift) / scale, ldj -= sum log scale
-        mbar_wait(BAR(B_OFULL + wg), par);
-        tc_fence_after();
-        TR(9);
-        {
-          uint32_t sh[32];
-          tmem_ld32(tm_o, sh);
-          if (scaled) {
-            uint32_t sc[32];
-            tmem_ld32(tm_o + 32, sc);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k0 = 0; k0 < U; k0 += 8) {
-              float prod = 1.f;  // 8 factors in [1e-3, 1e3] stay inside the float32 range
-#pragma unroll
-              for (int k = k0; k < k0 + 8; ++k) {
-                const float shift = __uint_as_float(sh[k]) + b2[k];
-                const float a = __uint_as_float(sc[k]) + b2[U + k];
-                float s = softplus_clip_fast(a);
-                s = (a != a) ? a : s;  // keep NaN (fminf/fmaxf would drop it)
-                y[DH + k] = (y[DH + k] - shift) * rcp_approx(s);
-                prod *= s;
-              }
-              ldj -= 0.6931471805599453f * lg2_approx(prod);
-            }
-          } else {
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < U; ++k) y[DH + k] -= __uint_as_float(sh[k]) + b2[k];
-          }
-        }
-        if (l + 1 < nl) {
-          // feature (logical 32) is frozen from here on: it is the new conditioning column l of the
-          // following layers
-          const float v = y[DH];
-          const uint16_t hs16 = to_f16(v * H2_SCALE);
-          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 8 * 2048 + tid * 16 + l * 2) = to_f16(fmaf(from_f16(hs16), -H2_INV, v));
-          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 9 * 2048 + tid * 16 + l * 2) = hs16;
-          // inverse of tfb.Permute([D-1, 0, .., D-2]): rotate left by one (flows.py:65-66)
-          const float y0 = y[0];
-#pragma unroll
-          for (int i = 0; i < D - 1; ++i) y[i] = y[i + 1];
-          y[D - 1] = y0;
-        }
-        TR(10);
-      }
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const float z = y[i] * invT;
-        ss = fmaf(z, z, ss);
-      }
-      const float lnphi = -0.5f * ss + base_const + ldj - P.sum_log_amp;
-      if (live && lnpred_out) lnpred_out[r] = lnphi;
-      if (FOLD) {
-        float a[1] = {lnphi};
-        float bb[1] = {live ? (float)lnpost[r] : 0.f};
-        long long t1 = t0 + TILE;
-        if (t1 > row_hi) t1 = row_hi;
-        if (t0 < row_hi) fold.tile<1>(t0, t1, a, bb);
-      }
-    }
-    if (FOLD) fold.finish(had_rows);
   } else {
-    // ===== epilogue warpgroups, NT = 3 =====
-    // 128 registers per thread: features are owned by ORIGINAL index and nothing rotates.  yt[i] = feature 32 + i,
+    // ===== epilogue warpgroups =====
+    // Features are owned by ORIGINAL index and nothing rotates.  yt[i] = feature 32 + i,
     // x7[i] = feature i < 7 (feature i joins the transformed half from layer i + 1 on); the features that no layer
     // touches (7..31) only contribute their squares, summed at the tile start.  At layer l feature f is GEMM2 output
     // column k = (f - 32 - l) mod 64, so O is read at a column offset of -l: entry i of the 32-column load is
@@ -835,14 +640,15 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     const float invT = 1.f / P.T;
     const float base_const = -(float)D * logf(P.T) - 0.5f * (float)D * 1.8378770664093453f;
     constexpr int NX = MAX_TC_LAYERS - 1;  // features that can enter the transformed half
-    uint32_t it = 0, sc_it = 0;
+    uint32_t it = 0, pit = 0;
+    unsigned int nguard = 0;
 
     for (int b = 0; b < P.nbatches; ++b) {
       const long long t0 = row_lo + (long long)b * TILE;
       const long long r = t0 + tid;
       const bool live = r < row_hi;
       const long long rr = live ? r : 0;
-      float yt[U], x7[NX], ss = 0.f;
+      float yt[U], x7[NX], ss = 0.f, gmax = 0.f, gnew = 0.f;
       TR(1);
       {
         float y[D];
@@ -854,7 +660,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         }
 #pragma unroll
         for (int i = 0; i < D; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
-        // A operand, written once per tile (layout as in the NT = 2 branch)
+        // A operand, written once per tile: chunk c = columns 8 c .. 8 c + 7 (lo), chunk 4 + c the same columns (hs)
 #pragma unroll
         for (int c = 0; c < DH / 8; ++c) {
           uint4 plo, phi;
@@ -863,18 +669,17 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float va = y[8 * c + 2 * q], vb = y[8 * c + 2 * q + 1];
-            const uint32_t hs = pack_f16x2(vb * H2_SCALE, va * H2_SCALE);
-            const float2 bk = unpack_f16x2(hs);
-            ql[q] = pack_f16x2(fmaf(bk.y, -H2_INV, vb), fmaf(bk.x, -H2_INV, va));
-            qh[q] = hs;
+            split_x_pair(va, vb, qh[q], ql[q]);
+            gmax = fmaxf(gmax, fmaxf(fabsf(va), fabsf(vb)));  // fmaxf drops NaN: NaN rows do not trip the guard
           }
-          *reinterpret_cast<uint4*>(a1 + A_HALF + c * 2048 + tid * 16) = plo;
-          *reinterpret_cast<uint4*>(a1 + A_HALF + (4 + c) * 2048 + tid * 16) = phi;
+          *reinterpret_cast<uint4*>(a1 + c * 2048 + tid * 16) = plo;
+          *reinterpret_cast<uint4*>(a1 + (4 + c) * 2048 + tid * 16) = phi;
         }
         {
+          // new columns: none yet; the constant-one column (the 8th) is hs = fp16(SX) = 0x2800, lo = 0
           const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(a1 + A_HALF + 8 * 2048 + tid * 16) = z;
-          *reinterpret_cast<uint4*>(a1 + A_HALF + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x10000000u);
+          *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = z;
+          *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x28000000u);
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) x7[i] = y[i];
@@ -890,12 +695,11 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       for (int l = 0; l < nl; ++l, ++it) {
         const uint32_t par = it & 1;
         const bool scaled = l < P.nscaled;
-        const float* bl = bias_s + l * 64 - l;  // bl[i] = bt[i - l], bl[32 + i] = bt[32 - l + i] = bs[i - l], bl[64 + i] = bs[32 - l + i]
         fence_proxy_async();
         tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
         mbar_arrive(BAR(B_A1FULL + wg));
         TR(2);
-        // ---- E1 (as in the NT = 2 branch)
+        // ---- E1
         mbar_wait(BAR(B_HFULL + wg), par);
         tc_fence_after();
         TR(3);
@@ -922,7 +726,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           }
         }
         // ---- E2
-        mbar_wait(BAR(B_OFULL + wg), par);
+        mbar_wait(BAR(B_OFULL + wg), pit & 1);
+        ++pit;
         tc_fence_after();
         TR(9);
         if (!scaled) {
@@ -930,15 +735,17 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           tmem_ld32(tm_o - l, v0);
           tmem_ld8(tm_o + U - l, v1);
           tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(BAR(B_OCONS + wg));
 #pragma unroll
           for (int i = 0; i < U; ++i) {
-            const float shift = __uint_as_float(v0[i]) + bl[i];
-            yt[i] -= (i >= NX || i >= l) ? shift : 0.f;
+            const float yn = fmaf(__uint_as_float(v0[i]), -SO_INV, yt[i]);
+            yt[i] = (i >= NX || i >= l) ? yn : yt[i];
           }
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
-            const float shift = __uint_as_float(v1[i]) + bl[U + i];
-            x7[i] -= (i < l) ? shift : 0.f;
+            const float xn = fmaf(__uint_as_float(v1[i]), -SO_INV, x7[i]);
+            x7[i] = (i < l) ? xn : x7[i];
           }
         } else {
           // Scaled layer: O holds the SCALE pre-activations first.  Once they are in registers the MMA warp may
@@ -957,7 +764,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 #pragma unroll
             for (int i = k0; i < k0 + 8; ++i) {
               const bool act = i >= NX || i >= l;
-              const float a = __uint_as_float(v0[i]) + bl[U + i];
+              const float a = __uint_as_float(v0[i]) * SO_INV;
               float sc = softplus_clip_fast(a);
               sc = (a != a) ? a : sc;  // keep NaN (fminf/fmaxf would drop it)
               v0[i] = __float_as_uint(rcp_approx(sc));
@@ -970,7 +777,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
               if (i < l) {
-                const float a = __uint_as_float(v1[i]) + bl[2 * U + i];
+                const float a = __uint_as_float(v1[i]) * SO_INV;
                 float sc = softplus_clip_fast(a);
                 sc = (a != a) ? a : sc;
                 v1[i] = __float_as_uint(rcp_approx(sc));
@@ -981,40 +788,41 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           }
           // shifts (second MMA pass), in two 16-column loads + the columns of the entered features
           TR(11);
-          mbar_wait(BAR(B_OFULL2 + wg), sc_it & 1);
+          mbar_wait(BAR(B_OFULL + wg), pit & 1);
+          ++pit;
           tc_fence_after();
           TR(12);
-          ++sc_it;
           uint32_t w0[16], w1[8];
           tmem_ld16(tm_o - l, w0);
           tmem_ld8(tm_o + U - l, w1);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float yn = (yt[i] - (__uint_as_float(w0[i]) + bl[i])) * __uint_as_float(v0[i]);
+            const float yn = fmaf(__uint_as_float(w0[i]), -SO_INV, yt[i]) * __uint_as_float(v0[i]);
             yt[i] = (i >= NX || i >= l) ? yn : yt[i];
           }
           tmem_ld16(tm_o - l + 16, w0);
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
-            const float xn = (x7[i] - (__uint_as_float(w1[i]) + bl[U + i])) * __uint_as_float(v1[i]);
+            const float xn = fmaf(__uint_as_float(w1[i]), -SO_INV, x7[i]) * __uint_as_float(v1[i]);
             x7[i] = (i < l) ? xn : x7[i];
           }
           tmem_ld_wait16(w0);
+          tc_fence_before();
+          mbar_arrive(BAR(B_OCONS + wg));
 #pragma unroll
-          for (int i = 16; i < U; ++i) {
-            const float yn = (yt[i] - (__uint_as_float(w0[i - 16]) + bl[i])) * __uint_as_float(v0[i]);
-            yt[i] = yn;  // features 48.. are transformed by every layer
-          }
+          for (int i = 16; i < U; ++i)  // features 48.. are transformed by every layer
+            yt[i] = fmaf(__uint_as_float(w0[i - 16]), -SO_INV, yt[i]) * __uint_as_float(v0[i]);
         }
         if (l + 1 < nl) {
           // feature 32 + l is final from here on: it is the new conditioning column l of the following layers
           float v = yt[0];
 #pragma unroll
           for (int i = 1; i < NX; ++i) v = (l == i) ? yt[i] : v;
-          const uint16_t hs16 = to_f16(v * H2_SCALE);
-          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 8 * 2048 + tid * 16 + l * 2) = to_f16(fmaf(from_f16(hs16), -H2_INV, v));
-          *reinterpret_cast<uint16_t*>(a1 + A_HALF + 9 * 2048 + tid * 16 + l * 2) = hs16;
+          gnew = fmaxf(gnew, fabsf(v));
+          const uint16_t hs16 = to_f16(v * SX);
+          *reinterpret_cast<uint16_t*>(a1 + 8 * 2048 + tid * 16 + l * 2) = to_f16(fmaf(from_f16(hs16), -SX_INV, v));
+          *reinterpret_cast<uint16_t*>(a1 + 9 * 2048 + tid * 16 + l * 2) = hs16;
         }
         TR(10);
       }
@@ -1029,6 +837,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         ss = fmaf(z, z, ss);
       }
       const float lnphi = -0.5f * ss + base_const + ldj - P.sum_log_amp;
+      nguard += (live && (gmax > P.guard_raw || gnew > P.guard_all)) ? 1u : 0u;
       if (live && lnpred_out) lnpred_out[r] = lnphi;
       if (FOLD) {
         float a[1] = {lnphi};
@@ -1039,6 +848,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       }
     }
     if (FOLD) fold.finish(had_rows);
+    if (P.guard && nguard) atomicAdd(P.guard, (unsigned long long)nguard);
   }
 #ifdef HB_TC_TRACE
   if (tr_on) g_trace_n[tr_s] = tr_n;
@@ -1064,9 +874,10 @@ extern "C" __attribute__((visibility("default"))) int hb_debug_trace_read(unsign
 #endif
 
 // ---------------------------------------------------------------------------------------------
-// host side: weight image (hi/lo split, canonical K-major no-swizzle layout, 16 KiB chunks)
+// host side: weight image (hi/lo split, canonical K-major no-swizzle layout, SLOT_BYTES chunks)
 // ---------------------------------------------------------------------------------------------
-static inline void split_tf32(float v, float* hi, float* lo) {
+// w = hi + lo, hi = the 11 leading significant bits (truncated), lo exact in float32
+static inline void split_hi_lo(float v, float* hi, float* lo) {
   uint32_t b;
   memcpy(&b, &v, 4);
   b &= 0xffffe000u;
@@ -1080,15 +891,18 @@ static inline size_t kmajor_off16(int N, int n, int k) {
   return (size_t)(n / 8) * 64 + (size_t)(n % 8) * 8 + (size_t)(k / 8) * (N * 8) + (k % 8);
 }
 
-// float -> IEEE half, round to nearest even, saturating to +-65504 (NaN stays NaN)
-static inline uint16_t f32_to_f16(float f) {
+// float -> IEEE half, round to nearest even; *overflow is set when the value does not fit (NaN stays NaN)
+static inline uint16_t f32_to_f16(float f, bool* overflow) {
   uint32_t x;
   memcpy(&x, &f, 4);
   const uint32_t sign = (x >> 16) & 0x8000u;
   const uint32_t absx = x & 0x7fffffffu;
   if (absx > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);
-  if (absx >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);  // >= 65520 rounds past the largest half
-  if (absx < 0x33000001u) return (uint16_t)sign;                // < 2^-25 (rounds to zero)
+  if (absx >= 0x477ff000u) {  // >= 65520 rounds past the largest half
+    *overflow = true;
+    return (uint16_t)(sign | 0x7bffu);
+  }
+  if (absx < 0x33000001u) return (uint16_t)sign;  // < 2^-25 (rounds to zero)
   const int e = (int)(absx >> 23) - 127;
   uint32_t mant = (absx & 0x7fffffu) | 0x800000u;
   if (e < -14) {  // subnormal half: value = mant * 2^(e-23), unit = 2^-24
@@ -1108,15 +922,43 @@ static inline uint16_t f32_to_f16(float f) {
   return (uint16_t)(sign | (he << 10) | (q & 0x3ffu));
 }
 
-// one weight w = hi + lo (hi: 11 significant bits) into the three FP16 operands: m16[off_main] = fp16(hi * 2^11)
-// (main term, meets hs), h16[off_hi] = fp16(hi) (meets lo), h16[off_lo] = fp16(lo * 2^11) (meets hs)
-static inline void put_weight(float w, uint16_t* m16, size_t off_main, uint16_t* h16, size_t off_hi, size_t off_lo) {
-  float hi, lo;
-  split_tf32(w, &hi, &lo);
-  m16[off_main] = f32_to_f16(hi * 2048.0f);
-  h16[off_hi] = f32_to_f16(hi);
-  h16[off_lo] = f32_to_f16(lo * 2048.0f);
-}
+namespace {
+
+// The GEMM1-shaped blocks of an effective [KA x n_out] weight matrix M (row k multiplies A operand column k: 32
+// raw inputs, 7 new columns, the constant one) for output rows [n0, n0 + n_out) of a block that is N rows wide,
+// result scale `so` (1 for H, SO for O):
+//   ga: [N x 64 K']: K' = k hi so (meets lo), K' = 32 + k lo so / SX (meets hs)           -- raw inputs k < 32
+//   gb: [N x 32 K']: K' = k hi so / SX (meets hs)
+//   gc: [N x 16 K'] x 2: block 0 K' = c hi so (meets lo new), K' = 8 + c lo so / SX; block 1 K' = 8 + c hi so / SX
+struct Gemm1Writer {
+  uint16_t *ga, *gb, *gc;
+  int N;
+  bool overflow = false;
+  void put(const std::vector<double>& M, int n_out, int n0, float so) {
+    for (int k = 0; k < tc::KA; ++k)
+      for (int n = 0; n < n_out; ++n) {
+        const float w = (float)M[(size_t)k * n_out + n];
+        float hi, lo;
+        split_hi_lo(w, &hi, &lo);
+        const uint16_t h_plain = f32_to_f16(hi * so, &overflow), h_main = f32_to_f16(hi * so * tc::SX_INV, &overflow),
+                       l_main = f32_to_f16(lo * so * tc::SX_INV, &overflow);
+        const int row = n0 + n;
+        if (k < 32) {
+          ga[kmajor_off16(N, row, k)] = h_plain;
+          ga[kmajor_off16(N, row, 32 + k)] = l_main;
+          gb[kmajor_off16(N, row, k)] = h_main;
+        } else {
+          const int c = k - 32;
+          gc[kmajor_off16(N, row, c)] = h_plain;
+          gc[kmajor_off16(N, row, 8 + c)] = l_main;
+          gc[(size_t)N * 16 + kmajor_off16(N, row, c)] = 0;
+          gc[(size_t)N * 16 + kmajor_off16(N, row, 8 + c)] = h_main;
+        }
+      }
+  }
+};
+
+}  // namespace
 
 int realnvp_tc_prepare(Flow* f) {
   f->tc_ok = false;
@@ -1125,21 +967,15 @@ int realnvp_tc_prepare(Flow* f) {
   const int nl = f->nlayers;
   if (nl > tc::MAX_TC_LAYERS) return HB_OK;
   const int d = f->d, u = f->u;
-  // weights (and b0, which rides in W0') are stored * 2^11 as halves: |w| must stay below 65504 / 2048 (else the
-  // CUDA-core path runs)
-  for (int l = 0; l < nl; ++l) {
-    const float* W0 = f->host_weights.data() + f->layer_off[l];
-    const size_t n2 = (size_t)d * 128 + 128 + (size_t)128 * u * ((l < ds.n_scaled) ? 2 : 1) + u;  // W0, b0, Wt, bt, (Ws)
-    for (size_t i = 0; i < n2; ++i)
-      if (!(fabsf(W0[i]) < 16.0f)) return HB_OK;
-  }
-  const size_t CF = tc::SLOT_BYTES / 4;  // floats per chunk
+  if (d != tc::DH || u != tc::U) return HB_OK;
+  const double alpha = 0.5 * (1.0 + tc::LEAKY_SLOPE), beta = 0.5 * (1.0 - tc::LEAKY_SLOPE);
   size_t nchunks = 0;
-  for (int l = 0; l < nl; ++l) nchunks += (l < ds.n_scaled) ? 7 : 5;
-  std::vector<float> img(nchunks * CF, 0.f);
-  std::vector<float> bias((size_t)nl * 64, 0.f);
+  for (int l = 0; l < nl; ++l) nchunks += tc::layer_chunks(l < ds.n_scaled);
+  std::vector<uint8_t> img(nchunks * tc::SLOT_BYTES, 0);
   const float* w = f->host_weights.data();
   size_t ch = 0;
+  bool overflow = false;
+  double hsum_max = 0.0, hbias_max = 0.0;  // |H| <= hsum_max * max|x'| + hbias_max
   for (int l = 0; l < nl; ++l) {
     const bool scaled = l < ds.n_scaled;
     const float* W0 = w + f->layer_off[l];       // [d][128]
@@ -1148,99 +984,102 @@ int realnvp_tc_prepare(Flow* f) {
     const float* bt = Wt + (size_t)128 * u;
     const float* Ws = bt + u;
     const float* bs = Ws + (size_t)128 * u;
-    // GEMM1 main: A column i (original feature i < 32) meets W0 row i - l (zero for i < l).
-    // chunk 0: FP16 [128 x 32 K'] fp16(hi * 2^11); chunk 1: FP16 [128 x 64 K']: K' < 32 fp16(hi), K' >= 32
-    // fp16(lo * 2^11)
-    {
-      uint16_t* c0 = reinterpret_cast<uint16_t*>(img.data() + ch * CF);
-      uint16_t* c1 = reinterpret_cast<uint16_t*>(img.data() + (ch + 1) * CF);
-      for (int i = 0; i < 32; ++i)
-        for (int n = 0; n < 128; ++n) {
-          const float v = (i >= l) ? W0[(size_t)(i - l) * 128 + n] : 0.f;
-          put_weight(v, c0, kmajor_off16(128, n, i), c1, kmajor_off16(128, n, i), kmajor_off16(128, n, 32 + i));
-        }
+    // W0eff[k][j]: A column k (original feature k < 32; new column c = k - 32 = frozen feature 32 + c; constant) meets
+    // W0 row k - l (zero for k < l) / row 32 - l + c (c < l) / b0
+    std::vector<double> W0eff((size_t)tc::KA * 128, 0.0);
+    for (int j = 0; j < 128; ++j) {
+      for (int k = l; k < 32; ++k) W0eff[(size_t)k * 128 + j] = W0[(size_t)(k - l) * 128 + j];
+      for (int c = 0; c < l && c < 7; ++c) W0eff[(size_t)(32 + c) * 128 + j] = W0[(size_t)(32 - l + c) * 128 + j];
+      W0eff[(size_t)39 * 128 + j] = b0[j];
+      double s = 0.0;
+      for (int k = 0; k < 39; ++k) s += fabs(W0eff[(size_t)k * 128 + j]);
+      if (s > hsum_max) hsum_max = s;
+      if (fabs((double)b0[j]) > hbias_max) hbias_max = fabs((double)b0[j]);
     }
-    // GEMM1 correction (chunk 2): k = 0..6 <-> frozen feature 32 + j meets W0 row 32 - l + j (j < l),
-    // k = 7 <-> constant-one column carrying the bias b0.  FP16 [128 x 16 K'] 4 KB: K' < 8 zero (meets lo new),
-    // K' >= 8 fp16(hi * 2^11) (meets hs new) | FP16 [128 x 16 K'] 4 KB: fp16(hi) | fp16(lo * 2^11)
-    {
-      uint16_t* c = reinterpret_cast<uint16_t*>(img.data() + (ch + 2) * CF);
-      uint16_t* ch16 = c + 2048;
-      for (int k = 0; k < 8; ++k)
-        for (int n = 0; n < 128; ++n) {
-          float v = 0.f;
-          if (k == 7) v = b0[n];
-          else if (k < l) v = W0[(size_t)(32 - l + k) * 128 + n];
-          put_weight(v, c, kmajor_off16(128, n, 8 + k), ch16, kmajor_off16(128, n, k), kmajor_off16(128, n, 8 + k));
+    // V[k][n] = alpha sum_j W0eff[k][j] W2[j][n]  (+ b2[n] on the constant row)
+    auto make_v = [&](const float* W2, const float* b2) {
+      std::vector<double> V((size_t)tc::KA * u, 0.0);
+      for (int k = 0; k < tc::KA; ++k)
+        for (int n = 0; n < u; ++n) {
+          double s = 0.0;
+          for (int j = 0; j < 128; ++j) s += W0eff[(size_t)k * 128 + j] * (double)W2[(size_t)j * u + n];
+          V[(size_t)k * u + n] = alpha * s + (k == 39 ? (double)b2[n] : 0.0);
         }
+      return V;
+    };
+    const std::vector<double> Vt = make_v(Wt, bt);
+    uint8_t* base = img.data() + ch * tc::SLOT_BYTES;
+    {
+      Gemm1Writer wr{reinterpret_cast<uint16_t*>(base), reinterpret_cast<uint16_t*>(base + tc::SLOT_BYTES),
+                     reinterpret_cast<uint16_t*>(base + tc::SLOT_BYTES + tc::GB_MAIN_BYTES), tc::N1};
+      wr.put(W0eff, 128, 0, 1.0f);
+      wr.put(scaled ? make_v(Ws, bs) : Vt, u, 128, tc::SO);
+      overflow |= wr.overflow;
     }
-    // GEMM2: B[n][k] = [Wt | Ws][k][n]; one K = 32 quarter = FP16 block [N2 x 96 K']: K' < 32 fp16(w_hi) (meets
-    // lo), 32..63 fp16(w_lo * 2^11), 64..95 fp16(w_hi * 2^11) (both meet hs = fp16(h * 2^-11)).  12 K'-chunks of 8 halves:
-    // 192 N2 bytes per quarter, one quarter per 16 KiB slot for scaled layers, two for unscaled ones.
+    // GEMM2: one K = 32 quarter = FP16 block [N2 x 96 K'] of u = beta W2 scaled by SO: K' < 32 -u_hi (meets hs - |H|),
+    // 32..63 u_lo, 64..95 u_hi (both meet hs).  Scaled layers: rows 0..31 shift, 32..63 scale, one quarter per chunk;
+    // unscaled layers: two quarters per chunk.
     const int N2 = scaled ? 64 : 32;
-    const size_t qh = (size_t)12 * N2 * 8;  // halves per quarter block
     for (int q = 0; q < 4; ++q) {
-      uint16_t* c16 = reinterpret_cast<uint16_t*>(scaled ? img.data() + (ch + 3 + q) * CF
-                                                         : img.data() + (ch + 3 + (q >> 1)) * CF) +
-                      ((!scaled && (q & 1)) ? qh : 0);
+      uint16_t* c16 = reinterpret_cast<uint16_t*>(base + (size_t)(2 + (scaled ? q : (q >> 1))) * tc::SLOT_BYTES +
+                                                  ((!scaled && (q & 1)) ? tc::Q32_BYTES : 0));
       for (int kk = 0; kk < 32; ++kk)
         for (int n = 0; n < N2; ++n) {
           const int k = 32 * q + kk;
-          const float v = (n < u) ? Wt[(size_t)k * u + n] : Ws[(size_t)k * u + (n - u)];
+          const float v = (float)(beta * (double)((n < u) ? Wt[(size_t)k * u + n] : Ws[(size_t)k * u + (n - u)]));
           float hi, lo;
-          split_tf32(v, &hi, &lo);
-          c16[kmajor_off16(N2, n, kk)] = f32_to_f16(hi);
-          c16[kmajor_off16(N2, n, 32 + kk)] = f32_to_f16(lo * 2048.0f);
-          c16[kmajor_off16(N2, n, 64 + kk)] = f32_to_f16(hi * 2048.0f);
+          split_hi_lo(v, &hi, &lo);
+          c16[kmajor_off16(N2, n, kk)] = f32_to_f16(-hi * tc::SO, &overflow);
+          c16[kmajor_off16(N2, n, 32 + kk)] = f32_to_f16(lo * tc::SO, &overflow);
+          c16[kmajor_off16(N2, n, 64 + kk)] = f32_to_f16(hi * tc::SO, &overflow);
         }
     }
-    ch += scaled ? 7 : 5;
-    for (int k = 0; k < u; ++k) bias[(size_t)l * 64 + k] = bt[k];
-    if (scaled)
-      for (int k = 0; k < u; ++k) bias[(size_t)l * 64 + u + k] = bs[k];
+    if (scaled) {
+      uint8_t* vt = base + (size_t)6 * tc::SLOT_BYTES;
+      Gemm1Writer wr{reinterpret_cast<uint16_t*>(vt), reinterpret_cast<uint16_t*>(vt + u * 64 * 2),
+                     reinterpret_cast<uint16_t*>(vt + u * 96 * 2), u};
+      wr.put(Vt, u, 0, tc::SO);
+      overflow |= wr.overflow;
+    }
+    ch += tc::layer_chunks(scaled);
   }
-  const size_t img_bytes = img.size() * 4, bias_bytes = bias.size() * 4;
-  HB_CUDA(cudaMalloc(&f->tc_image, img_bytes + bias_bytes));
-  HB_CUDA(cudaMemcpy(f->tc_image, img.data(), img_bytes, cudaMemcpyHostToDevice));
-  HB_CUDA(cudaMemcpy((char*)f->tc_image + img_bytes, bias.data(), bias_bytes, cudaMemcpyHostToDevice));
-  f->tc_image_bytes = img_bytes;
+  if (overflow) return HB_OK;  // a weight block leaves the half range: the CUDA-core path serves this flow
+  // range guard: hs = fp16(|H|) must stay finite (|H| <= hsum_max |x'|_max + |b0|_max), and beyond ~32 standardised
+  // units the truncating accumulator shows (tests/test_gpu_flows.py::test_realnvp_tcgen05_large_magnitude)
+  double hard = 1e30;
+  if (hsum_max > 0.0) hard = (60000.0 - hbias_max) / hsum_max;
+  if (!(hard > 1.0)) return HB_OK;
+  f->tc_guard_all = (float)hard;
+  f->tc_guard_raw = (float)(hard < 32.0 ? hard : 32.0);
+  HB_CUDA(cudaMalloc(&f->tc_image, img.size()));
+  HB_CUDA(cudaMemcpy(f->tc_image, img.data(), img.size(), cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMalloc(&f->tc_guard, sizeof(unsigned long long)));
+  HB_CUDA(cudaMemset(f->tc_guard, 0, sizeof(unsigned long long)));
+  f->tc_image_bytes = img.size();
   f->tc_ok = true;
   return HB_OK;
 }
 
 void realnvp_tc_release(Flow* f) {
   if (f->tc_image) cudaFree(f->tc_image);
+  if (f->tc_guard) cudaFree(f->tc_guard);
   f->tc_image = nullptr;
-}
-
-// tiles in flight per CTA: HB_TC_TILES = 2 | 3 (A/B measurements)
-static int tc_tiles() {
-  static const int v = [] {
-    const char* e = getenv("HB_TC_TILES");
-    return (e && e[0] == '2') ? 2 : 3;
-  }();
-  return v;
+  f->tc_guard = nullptr;
 }
 
 template <typename XT, typename LT, bool FOLD>
 static int tc_launch(const tc::Params& P, int grid, const void* x, long long ld, const void* lnpost,
                      float* lnpred_out, const FoldParams& fp, cudaStream_t st) {
-  if (tc_tiles() == 3) {
-    auto kern = tc::realnvp_tc_kernel<XT, LT, FOLD, 3>;
-    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::L<3>::SM_TOTAL));
-    kern<<<grid, tc::L<3>::THREADS, tc::L<3>::SM_TOTAL, st>>>(P, (const XT*)x, ld, (const LT*)lnpost, lnpred_out, fp);
-  } else {
-    auto kern = tc::realnvp_tc_kernel<XT, LT, FOLD, 2>;
-    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::L<2>::SM_TOTAL));
-    kern<<<grid, tc::L<2>::THREADS, tc::L<2>::SM_TOTAL, st>>>(P, (const XT*)x, ld, (const LT*)lnpost, lnpred_out, fp);
-  }
+  auto kern = tc::realnvp_tc_kernel<XT, LT, FOLD>;
+  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
+  kern<<<grid, tc::THREADS, tc::SM_TOTAL, st>>>(P, (const XT*)x, ld, (const LT*)lnpost, lnpred_out, fp);
   return HB_OK;
 }
 
 int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
                    const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
                    const int64_t* start, long long chain_lo, long long chain_hi, long long a,
-                   long long b, cudaStream_t st) {
+                   long long b, unsigned long long* guard, cudaStream_t st) {
   if (!f->tc_ok) {
     set_error("tcgen05 path not available for this flow");
     return HB_ERR_UNSUPPORTED;
@@ -1248,7 +1087,7 @@ int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, l
   if (n <= 0) return HB_OK;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-  const int NWG = tc_tiles();
+  const int NWG = tc::NT;
   long long nwg = (long long)sms * NWG;
   long long rpw = (n + nwg - 1) / nwg;
   rpw = ((rpw + tc::TILE - 1) / tc::TILE) * tc::TILE;
@@ -1257,13 +1096,14 @@ int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, l
   const long long nfl = (long long)grid * NWG;
   tc::Params P;
   P.image = static_cast<const uint8_t*>(f->tc_image);
-  P.bias = reinterpret_cast<const float*>(static_cast<const char*>(f->tc_image) + f->tc_image_bytes);
   P.pre = f->desc.standardize ? f->dev_weights : nullptr;
   P.nlayers = f->nlayers;
   P.nscaled = f->desc.n_scaled;
   P.T = T;
   P.sum_log_amp = f->sum_log_amp;
-  P.chunks_per_batch = (int)(f->tc_image_bytes / tc::SLOT_BYTES);
+  P.guard = guard;
+  P.guard_raw = f->tc_guard_raw;
+  P.guard_all = f->tc_guard_all;
   P.nrows = n;
   P.rows_per_wg = rpw;
   P.nbatches = (int)(rpw / tc::TILE);
