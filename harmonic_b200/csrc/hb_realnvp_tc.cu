@@ -8,7 +8,7 @@
 //   3 epilogue warpgroups : each owns one tile at a time, one sample per thread (TMEM lane = sample).  A thread keeps
 //                     the 32 initially transformed features + the 7 that can enter, owned by ORIGINAL index
 //   producer warp   : streams the pre-split weight image (FP16 blocks, UMMA canonical no-swizzle K-major layout,
-//                     built once on the host) from L2 into a 7-slot ring of 20 KiB chunks with cp.async.bulk + mbarrier
+//                     built once on the host) from L2 into a 7-slot ring of 20 KiB slots (3 - 4 chunks per layer) with cp.async.bulk + mbarrier
 //   3 MMA warps     : tcgen05.mma issuers, warp W_MMA + t serves tile t (the first also allocates TMEM); warp-uniform
 //                     straight-line program with blocking mbarrier waits, one elected lane issues.  One issuing warp
 //                     sustains one tcgen05.mma per ~49 cycles whatever N <= 64 is, while the tensor pipe itself needs
@@ -23,19 +23,20 @@
 //
 // Per coupling layer and tile
 //   GEMM1  [H | O] [128 x 160] = [x(0..31) | new(0..6) | 1] . [W0' | V]     A, B from shared memory, K = 40
-//   E1     |H| -> FP16 pair (hs, hs - |H|), in place of H                    eight 16-column chunks, loads prefetched
+//   E1     |H| -> FP16 pair (hs, |H| - hs), in place of H                    eight 16-column chunks, loads prefetched
 //   GEMM2  O[128 x 32] += |H|[:, quarter] . U[quarter, :]                    A from TMEM, 6 FP16 MMAs per K = 32 quarter
 //   E2     y -= O (shift) or softplus-clip scale epilogue on y, log-det
 // Scaled layers run GEMM1 with V_scale, GEMM2 with U_scale, hand O to the epilogue, then a second pass O = x' V_shift
 // (8 small MMAs) + |H| U_shift over the same operands, which runs under the softplus / reciprocal / log-det arithmetic.
 //
 // Split-precision contractions with FP32 accumulation in TMEM, float32-equivalent products (~2^-22), every MMA
-// kind::f16.  A weight is w_hi (11 significant bits) + w_lo; an activation a is hs = fp16(a s) (round to nearest) and
-// the exact remainder lo = a - hs / s, rounded to fp16:
-//     a w ~= hs (w_hi / s) + hs (w_lo / s) + lo w_hi                          (the lo w_lo term, <= 2^-22, dropped)
-// GEMM1: s = SX = 2^-5 for the conditioning inputs (written once per tile); GEMM2: s = 1, hs = fp16(|H|) straight out
-// of the accumulator and hs - |H| = -lo by ONE mixed-precision subtract (FHADD), against -u_hi.  O accumulates
-// SO = 2^5 times its value (so that u_lo and v_lo are normal halves); E2 removes the factor inside its FMA.
+// kind::f16.  A weight is w_hi (11 significant bits) + w_lo; an activation a is hs = fp16(a) (round to nearest) and
+// the exact remainder lo = a - hs, rounded to fp16:
+//     a w ~= hs w_hi + lo w_hi + hs w_lo                                       (the lo w_lo term, <= 2^-22, dropped)
+// with s = 1 everywhere: hs = fp16(a) straight out of the register / accumulator and lo = a - hs by ONE
+// mixed-precision FMA (FHFMA), both against the SAME hi block.  So that w_lo stays a normal half the weights travel
+// scaled: H accumulates SH = 2^5 times its value (|H| is positively homogeneous, E1 does not care), O accumulates
+// SO = 2^10 times its value; E2 removes the factor inside its FMA.
 // What remains against a float32 FMA chain is the tensor cores' truncating accumulator
 // (profiles/r1_tensor_accum_rounding.txt), see DESIGN.md 4.1.
 //
@@ -57,7 +58,7 @@
 // GEMM2 is pipelined with E1 at quarter granularity: quarter q's operands replace its own 32 H columns, its
 // GEMM2 step runs while the epilogue computes quarter q + 1 (one mbarrier per quarter: the epilogue may run a
 // whole layer ahead of the MMA warp, never two phases of one barrier).
-// TMEM: tile t at column 160 t: P (128: H, then per 16-column chunk 8 columns of packed -lo pairs + 8 of packed hs
+// TMEM: tile t at column 160 t: P (128: H, then per 16-column chunk 8 columns of packed lo pairs + 8 of packed hs
 // pairs) | O (32).
 #include <math.h>
 #include <stdlib.h>
@@ -82,22 +83,29 @@ constexpr int MAX_TC_LAYERS = 8;  // one K = 8 correction step holds 7 new colum
 constexpr int KA = 40;            // A operand columns: 32 raw + 7 new + 1 constant
 constexpr int A_TILE = KA / 4 * 2048;  // FP16 block, 10 chunks of 8 columns: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
 constexpr int N1 = 128 + U;       // GEMM1 output columns: H | O
-constexpr float SX = 0.03125f, SX_INV = 32.0f;  // conditioning inputs travel as hs = fp16(x SX)
-constexpr float SO = 32.0f, SO_INV = 0.03125f;  // O accumulates SO times its value
+constexpr float SH = 32.0f;                        // H accumulates SH times its value (so that w_lo is a normal half)
+constexpr float SU = 32.0f;                        // GEMM2 weights travel times SU (u_lo a normal half)
+constexpr float SO = SH * SU, SO_INV = 1.0f / SO;  // hence O accumulates SO times its value
 constexpr double LEAKY_SLOPE = 0.01;
 
-// weight image: per layer GA, GB, then GEMM2 chunks (unscaled: two quarters per chunk; scaled: one per chunk + VT)
-constexpr int GA_BYTES = N1 * 64 * 2;          // [160 x 64 K']: K' < 32 hi (meets lo), K' >= 32 lo / SX (meets hs)
-constexpr int GB_MAIN_BYTES = N1 * 32 * 2;     // [160 x 32 K']: hi / SX (meets hs)
-constexpr int GB_CORR_BYTES = N1 * 16 * 2;     // [160 x 16 K'] x 2: [hi ; lo / SX] and [0 ; hi / SX] over [lo new | hs new]
-constexpr int GB_BYTES = GB_MAIN_BYTES + 2 * GB_CORR_BYTES;
-constexpr int Q32_BYTES = 32 * 96 * 2;         // one K = 32 quarter, N2 = 32: K' < 32 -hi, 32..63 lo, 64..95 hi (all x SO)
-constexpr int Q64_BYTES = 64 * 96 * 2;         // scaled layers: rows 0..31 shift, 32..63 scale
-constexpr int VT_BYTES = U * (64 + 32 + 16 + 16) * 2;  // second pass of a scaled layer: the GEMM1 blocks of V_shift, N = 32
-static_assert(GA_BYTES <= SLOT_BYTES && GB_BYTES <= SLOT_BYTES && 2 * Q32_BYTES <= SLOT_BYTES && Q64_BYTES <= SLOT_BYTES, "slot");
-__host__ __device__ __forceinline__ constexpr int layer_chunks(bool scaled) { return scaled ? 7 : 4; }
+// weight image, per layer (FP16 blocks, hi = the 11 leading bits of a weight, lo = the rest; ONE hi block serves
+// both halves of an activation's split):
+//   chunk 0  GA   [160 x 64 K']: K' < 32 hi (meets lo raw AND hs raw), K' >= 32 lo (meets hs raw)
+//   chunk 1  GB   corrections [160 x 16 K'] x 2 over [lo new | hs new]: [0 ; lo], then [hi ; hi];
+//                 then unscaled layers: GEMM2 quarters 0, 1; scaled layers: VT = the GEMM1 blocks of V_shift (N = 32)
+//   chunk 2, (3)  GEMM2 quarters 2, 3 (unscaled) / 0, 1 and 2, 3 (scaled)
+//   a GEMM2 quarter (K = 32 hidden units) is [N2 x 64 K']: K' < 32 hi (meets hs - and lo), K' >= 32 lo (meets hs);
+//   scaled layers N2 = 64: rows 0..31 shift, 32..63 scale
+constexpr int GA_BYTES = N1 * 64 * 2;
+constexpr int GB_CORR_BYTES = N1 * 16 * 2;     // one correction block
+constexpr int Q32_BYTES = 32 * 64 * 2;
+constexpr int Q64_BYTES = 64 * 64 * 2;
+constexpr int VT_BYTES = U * (64 + 16 + 16) * 2;
+constexpr int GB_U_BYTES = 2 * GB_CORR_BYTES + 2 * Q32_BYTES, GB_S_BYTES = 2 * GB_CORR_BYTES + VT_BYTES;
+static_assert(GA_BYTES <= SLOT_BYTES && GB_U_BYTES <= SLOT_BYTES && GB_S_BYTES <= SLOT_BYTES && 2 * Q64_BYTES <= SLOT_BYTES, "slot");
+__host__ __device__ __forceinline__ constexpr int layer_chunks(bool scaled) { return scaled ? 4 : 3; }
 __host__ __device__ __forceinline__ constexpr uint32_t chunk_bytes(bool scaled, int j) {
-  return j == 0 ? GA_BYTES : j == 1 ? GB_BYTES : !scaled ? 2 * Q32_BYTES : j < 6 ? Q64_BYTES : VT_BYTES;
+  return j == 0 ? GA_BYTES : j == 1 ? (scaled ? GB_S_BYTES : GB_U_BYTES) : (scaled ? 2 * Q64_BYTES : 2 * Q32_BYTES);
 }
 
 constexpr int THREADS = NT * 128 + 32 * (NT + 1);  // + producer warp + one MMA warp per tile
@@ -341,65 +349,69 @@ __device__ __forceinline__ float softplus_clip_fast(float a) {
   return fminf(fmaxf(sp, 1e-3f), 1e3f);  // NaN in -> NaN out is handled by the caller's y1 path
 }
 
+// DH consecutive values of one sample row -> float32 registers (16-byte loads when the row allows)
 template <typename XT>
-__device__ __forceinline__ void load_row(const XT* __restrict__ x, long long ld, long long r, float (&y)[D]);
+__device__ __forceinline__ void load_half(const XT* __restrict__ p, float (&y)[DH]);
 
 template <>
-__device__ __forceinline__ void load_row<float>(const float* __restrict__ x, long long ld, long long r,
-                                                float (&y)[D]) {
-  const float* p = x + r * ld;
+__device__ __forceinline__ void load_half<float>(const float* __restrict__ p, float (&y)[DH]) {
   if ((((uintptr_t)p) & 15) == 0) {
 #pragma unroll
-    for (int i = 0; i < D / 4; ++i) {
+    for (int i = 0; i < DH / 4; ++i) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
       y[4 * i] = v.x; y[4 * i + 1] = v.y; y[4 * i + 2] = v.z; y[4 * i + 3] = v.w;
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < D; ++i) y[i] = __ldg(p + i);
+    for (int i = 0; i < DH; ++i) y[i] = __ldg(p + i);
   }
 }
 template <>
-__device__ __forceinline__ void load_row<double>(const double* __restrict__ x, long long ld, long long r,
-                                                 float (&y)[D]) {
-  const double* p = x + r * ld;
+__device__ __forceinline__ void load_half<double>(const double* __restrict__ p, float (&y)[DH]) {
   if ((((uintptr_t)p) & 15) == 0) {
 #pragma unroll
-    for (int i = 0; i < D / 2; ++i) {
+    for (int i = 0; i < DH / 2; ++i) {
       const double2 v = __ldg(reinterpret_cast<const double2*>(p) + i);
       y[2 * i] = (float)v.x; y[2 * i + 1] = (float)v.y;
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < D; ++i) y[i] = (float)__ldg(p + i);
+    for (int i = 0; i < DH; ++i) y[i] = (float)__ldg(p + i);
   }
 }
 
-// Split of a pair of conditioning inputs: hs = fp16(v SX) packed, lo = v - hs / SX (exact in float32, one
-// mixed-precision FMA each) packed.  hs is a normal half for |v| in [2^-9, 2.1e6]; below that lo carries the value.
-__device__ __forceinline__ void split_x_pair(float va, float vb, uint32_t& hs, uint32_t& lo) {
-  hs = pack_f16x2(vb * SX, va * SX);
-  float la, lb;
-  const uint16_t m = 0xD000;  // fp16(-SX_INV) = -32
+// a - hs for the two halves of a packed FP16 pair hs and two float32 values (exact: hs is a rounded to 11 bits), by
+// one mixed-precision FMA each (FHFMA: hs * -1 + a); with ABS the float32 operands enter as |a|
+template <bool ABS>
+__device__ __forceinline__ void split_rest(uint32_t hs, float a0, float a1, float& l0, float& l1) {
+  const uint16_t m1 = 0xBC00;  // fp16(-1)
+  if (ABS) {
+    a0 = fabsf(a0);
+    a1 = fabsf(a1);
+  }
   asm("{.reg .b16 a, b; mov.b32 {a, b}, %2; fma.rn.f32.f16 %0, a, %5, %3; fma.rn.f32.f16 %1, b, %5, %4;}"
-      : "=f"(la), "=f"(lb)
-      : "r"(hs), "f"(va), "f"(vb), "h"(m));
+      : "=f"(l0), "=f"(l1)
+      : "r"(hs), "f"(a0), "f"(a1), "h"(m1));
+}
+// Split of a pair of conditioning inputs: hs = fp16(v) packed, lo = fp16(v - hs) packed
+__device__ __forceinline__ void split_x_pair(float va, float vb, uint32_t& hs, uint32_t& lo) {
+  hs = pack_f16x2(vb, va);
+  float la, lb;
+  split_rest<false>(hs, va, vb, la, lb);
   lo = pack_f16x2(lb, la);
 }
 
-// E1 for one 16-column chunk of H: wh = 8 words of packed hs = fp16(|H|) pairs, wl = 8 words of packed fp16(hs - |H|)
-// pairs (= -lo, met by -u_hi in the weight image).  Per pair: F2FP, LOP3, 2 FHADD, F2FP.
+// E1 for one 16-column chunk of H: wh = 8 words of packed hs = fp16(|H|) pairs, wl = 8 words of packed fp16(|H| - hs)
+// pairs.  Per pair: F2FP, LOP3, 2 FHFMA, F2FP.
 __device__ __forceinline__ void e1_chunk(const uint32_t (&v)[16], uint32_t (&wl)[8], uint32_t (&wh)[8]) {
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
     const float h0 = __uint_as_float(v[2 * jj]), h1 = __uint_as_float(v[2 * jj + 1]);
     const uint32_t hs = pack_f16x2(h1, h0) & 0x7fff7fffu;
-    float n0, n1;
-    asm("{.reg .b16 a, b; mov.b32 {a, b}, %2; sub.rn.f32.f16 %0, a, %3; sub.rn.f32.f16 %1, b, %4;}"
-        : "=f"(n0), "=f"(n1)
-        : "r"(hs), "f"(fabsf(h0)), "f"(fabsf(h1)));
+    float l0, l1;
+    split_rest<true>(hs, h0, h1, l0, l1);
     wh[jj] = hs;
-    wl[jj] = pack_f16x2(n1, n0);
+    wl[jj] = pack_f16x2(l1, l0);
   }
 }
 
@@ -496,22 +508,20 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       mbar_wait(BAR(B_WFULL + (gidx % NSLOTS)), (gidx / NSLOTS) & 1);
     };
     auto chunk_addr = [&](uint32_t gidx) { return sbase + SM_RING + (gidx % NSLOTS) * SLOT_BYTES; };
-    // x' . B for the K = 32 raw inputs ("main") and the K = 8 new / constant columns ("corr"), B = GEMM1-shaped
-    // blocks of n output rows at ga (the [n x 64 K'] block), gb (the [n x 32 K'] block) and gb + 32 n 2 (corrections).
-    // Small terms first, then the main term.
-    auto issue_main = [&](uint32_t d, uint32_t ga, uint32_t gb, uint32_t n, uint32_t idesc, uint32_t acc0) {
-      const uint64_t wh = make_desc(ga, n * 16, 128), wt = make_desc(gb, n * 16, 128);
+    // x' . B for the K = 32 raw inputs ("main"): B = the [n x 64 K'] block at ga (hi | lo).  Small terms first
+    // (lo . hi, hs . lo), then the main term hs . hi
+    auto issue_main = [&](uint32_t d, uint32_t ga, uint32_t n, uint32_t idesc, uint32_t acc0) {
+      const uint64_t wh = make_desc(ga, n * 16, 128);
       const uint64_t kstep = (uint64_t)((n * 32) >> 4);
-      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma_ss_f16(d, adx + (uint64_t)(k * 256), wh + (uint64_t)k * kstep, idesc, k ? 1u : acc0);
+      for (int k = 0; k < 2; ++k) mma_ss_f16(d, adx + (uint64_t)(k * 256), wh + (uint64_t)k * kstep, idesc, k ? 1u : acc0);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) mma_ss_f16(d, adx + (uint64_t)((2 + k) * 256), wt + (uint64_t)k * kstep, idesc, 1);
-      }
-      __syncwarp();
+      for (int k = 0; k < 2; ++k) mma_ss_f16(d, adx + (uint64_t)((2 + k) * 256), wh + (uint64_t)(2 + k) * kstep, idesc, 1);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) mma_ss_f16(d, adx + (uint64_t)((2 + k) * 256), wh + (uint64_t)k * kstep, idesc, 1);
     };
+    // the K = 8 new / constant columns ("corr"): K' = 16 each over A = [lo new | hs new]: B = [0 ; lo], then [hi ; hi]
     auto issue_corr = [&](uint32_t d, uint32_t gc, uint32_t n, uint32_t idesc) {
-      // K' = 16 each over A = [lo new | hs new]: B = [hi ; lo / SX], then B = [0 ; hi / SX]
       const uint64_t wc = make_desc(gc, n * 16, 128);
       mma_ss_f16(d, adn, wc, idesc, 1);
       mma_ss_f16(d, adn, wc + (uint64_t)((n * 32) >> 4), idesc, 1);
@@ -526,8 +536,18 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         const uint32_t a_lo = a0 + 16 * half, a_hs = a_lo + 8;
         mma_ts_f16(tb + TM_O, a_lo, bd + (uint64_t)half * kstep2, ih32, 1);
         mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(2 + half) * kstep2, ih32, 1);
-        mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(4 + half) * kstep2, ih32, 1);
+        mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)half * kstep2, ih32, 1);
       }
+    };
+    // main part of a layer's GEMM1 (chunk g = GA), released as soon as its MMAs have completed
+    auto gemm1_main = [&](uint32_t g) {
+      wwait(g);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_main(tb + TM_P, chunk_addr(g), N1, ih1, 0);
+        tc_commit(BAR(B_WEMPTY + (g % NSLOTS)));
+      }
+      __syncwarp();
     };
     uint32_t g = 0, it = 0, pit = 0;
     for (int b = 0; b < P.nbatches; ++b) {
@@ -537,36 +557,30 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         // ---- GEMM1: (main, unless issued early) + correction
         mbar_wait(BAR(B_A1FULL + t), par);
         TR(20);
-        if (l == 0) {
-          wwait(g);
-          wwait(g + 1);
-          tc_fence_after();
-          issue_main(tb + TM_P, chunk_addr(g), chunk_addr(g + 1), N1, ih1, 0);
-        }
+        if (l == 0) gemm1_main(g);
         wwait(g + 1);
         tc_fence_after();
-        {
-          const uint32_t gc = chunk_addr(g + 1) + GB_MAIN_BYTES;
-          if (elect_one()) {
-            issue_corr(tb + TM_P, gc, N1, ih1);
-            tc_commit(BAR(B_HFULL + t));
-            tc_commit(BAR(B_WEMPTY + (g % NSLOTS)));
-            tc_commit(BAR(B_WEMPTY + ((g + 1) % NSLOTS)));
-          }
-          __syncwarp();
-          TR(21);
+        if (elect_one()) {
+          issue_corr(tb + TM_P, chunk_addr(g + 1), N1, ih1);
+          tc_commit(BAR(B_HFULL + t));
         }
+        __syncwarp();
+        TR(21);
         // ---- GEMM2: four K = 32 quarters, each as soon as its part of E1 has landed.  Scaled layers take the SCALE
         // rows (32..63 of each quarter block: + 4 row groups of 128 bytes) in this pass: their epilogue is the long one
         const uint32_t lbo2 = scaled ? 64u * 16u : 32u * 16u;
+        const uint32_t qbytes = scaled ? (uint32_t)Q64_BYTES : (uint32_t)Q32_BYTES;
+        // quarter q lives in chunk gq(q) at offset qoff(q)
+        auto gq = [&](int q) { return g + (scaled ? 2u : 1u) + (uint32_t)(q >> 1); };
+        auto qoff = [&](int q) { return ((!scaled && q < 2) ? (uint32_t)(2 * GB_CORR_BYTES) : 0u) + (uint32_t)(q & 1) * qbytes; };
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
-          const uint32_t gw = g + 2 + (scaled ? q : (q >> 1));
+          const uint32_t gw = gq(q);
           mbar_wait(BAR(B_A2 + NT * q + t), par);
           TR(22 + q);
           wwait(gw);
           tc_fence_after();
-          const uint32_t wbase = chunk_addr(gw) + ((!scaled && (q & 1)) ? (uint32_t)Q32_BYTES : 0u) + (scaled ? 512u : 0u);
+          const uint32_t wbase = chunk_addr(gw) + qoff(q) + (scaled ? 512u : 0u);
           if (elect_one()) {
             issue_quarter(q, wbase, lbo2);
             if (q == 3) tc_commit(BAR(B_OFULL + t));
@@ -580,24 +594,21 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           // read the scale pre-activations out of O
           mbar_wait(BAR(B_OCONS + t), pit & 1);
           ++pit;
-          wwait(g + 6);
           tc_fence_after();
           TR(32);
-          {
-            const uint32_t vt = chunk_addr(g + 6);
-            issue_main(tb + TM_O, vt, vt + U * 64 * 2, U, ih32, 0);
-            if (elect_one()) {
-              issue_corr(tb + TM_O, vt + U * 96 * 2, U, ih32);
+          if (elect_one()) {
+            const uint32_t vt = chunk_addr(g + 1) + 2 * GB_CORR_BYTES;
+            issue_main(tb + TM_O, vt, U, ih32, 0);
+            issue_corr(tb + TM_O, vt + U * 64 * 2, U, ih32);
 #pragma unroll 1
-              for (int q = 0; q < 4; ++q) {
-                issue_quarter(q, chunk_addr(g + 2 + q), lbo2);
-                tc_commit(BAR(B_WEMPTY + ((g + 2 + q) % NSLOTS)));
-              }
-              tc_commit(BAR(B_OFULL + t));
-              tc_commit(BAR(B_WEMPTY + ((g + 6) % NSLOTS)));
+            for (int q = 0; q < 4; ++q) {
+              issue_quarter(q, chunk_addr(gq(q)) + qoff(q), lbo2);
+              if (q & 1) tc_commit(BAR(B_WEMPTY + (gq(q) % NSLOTS)));
             }
-            __syncwarp();
+            tc_commit(BAR(B_OFULL + t));
+            tc_commit(BAR(B_WEMPTY + ((g + 1) % NSLOTS)));
           }
+          __syncwarp();
           TR(33);
         }
         g += layer_chunks(scaled);
@@ -607,10 +618,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         ++pit;
         TR(30);
         if (l + 1 < nl) {
-          wwait(g);
-          wwait(g + 1);
-          tc_fence_after();
-          issue_main(tb + TM_P, chunk_addr(g), chunk_addr(g + 1), N1, ih1, 0);
+          gemm1_main(g);
           TR(31);
         }
       }
@@ -650,16 +658,15 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       const long long rr = live ? r : 0;
       float yt[U], x7[NX], ss = 0.f, gmax = 0.f, gnew = 0.f;
       TR(1);
+      const XT* xrow = x + rr * ld;
+      float lp = 0.f;
+      if (FOLD) lp = live ? (float)lnpost[r] : 0.f;  // in flight until the fold at the end of the tile
       {
-        float y[D];
-        load_row<XT>(x, ld, rr, y);
-        if (r + TILE < row_hi) {  // pull the next tile's row into L2 while this tile computes
-          const char* nx = reinterpret_cast<const char*>(x + (r + TILE) * ld);
+        // conditioning half first: it is all the A operand needs; the transformed half is loaded under GEMM1 of layer 0
+        float y[DH];
+        load_half<XT>(xrow, y);
 #pragma unroll
-          for (int q = 0; q < (int)(D * sizeof(XT)); q += 128) prefetch_l2(nx + q);
-        }
-#pragma unroll
-        for (int i = 0; i < D; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
+        for (int i = 0; i < DH; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
         // A operand, written once per tile: chunk c = columns 8 c .. 8 c + 7 (lo), chunk 4 + c the same columns (hs)
 #pragma unroll
         for (int c = 0; c < DH / 8; ++c) {
@@ -676,10 +683,10 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           *reinterpret_cast<uint4*>(a1 + (4 + c) * 2048 + tid * 16) = phi;
         }
         {
-          // new columns: none yet; the constant-one column (the 8th) is hs = fp16(SX) = 0x2800, lo = 0
+          // new columns: none yet; the constant-one column (the 8th) is hs = fp16(1) = 0x3C00, lo = 0
           const uint4 z = make_uint4(0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = z;
-          *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x28000000u);
+          *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x3C000000u);
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) x7[i] = y[i];
@@ -688,8 +695,6 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           const float z = y[i] * invT;
           ss = fmaf(z, z, ss);
         }
-#pragma unroll
-        for (int i = 0; i < U; ++i) yt[i] = y[DH + i];
       }
       float ldj = 0.f;
       for (int l = 0; l < nl; ++l, ++it) {
@@ -699,6 +704,14 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
         mbar_arrive(BAR(B_A1FULL + wg));
         TR(2);
+        if (l == 0) {
+          load_half<XT>(xrow + DH, yt);  // raw; standardised below, once GEMM1 has been waited for
+          if (r + TILE < row_hi) {  // pull the next tile's row into L2 while this tile computes
+            const char* nx = reinterpret_cast<const char*>(x + (r + TILE) * ld);
+#pragma unroll
+            for (int q = 0; q < (int)(D * sizeof(XT)); q += 128) prefetch_l2(nx + q);
+          }
+        }
         // ---- E1
         mbar_wait(BAR(B_HFULL + wg), par);
         tc_fence_after();
@@ -724,6 +737,10 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
               TR(4 + q);
             }
           }
+        }
+        if (l == 0) {
+#pragma unroll
+          for (int i = 0; i < U; ++i) yt[i] = fmaf(yt[i], pre_s[DH + i], pre_s[D + DH + i]);
         }
         // ---- E2
         mbar_wait(BAR(B_OFULL + wg), pit & 1);
@@ -820,8 +837,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 #pragma unroll
           for (int i = 1; i < NX; ++i) v = (l == i) ? yt[i] : v;
           gnew = fmaxf(gnew, fabsf(v));
-          const uint16_t hs16 = to_f16(v * SX);
-          *reinterpret_cast<uint16_t*>(a1 + 8 * 2048 + tid * 16 + l * 2) = to_f16(fmaf(from_f16(hs16), -SX_INV, v));
+          const uint16_t hs16 = to_f16(v);
+          *reinterpret_cast<uint16_t*>(a1 + 8 * 2048 + tid * 16 + l * 2) = to_f16(v - from_f16(hs16));
           *reinterpret_cast<uint16_t*>(a1 + 9 * 2048 + tid * 16 + l * 2) = hs16;
         }
         TR(10);
@@ -841,7 +858,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       if (live && lnpred_out) lnpred_out[r] = lnphi;
       if (FOLD) {
         float a[1] = {lnphi};
-        float bb[1] = {live ? (float)lnpost[r] : 0.f};
+        float bb[1] = {lp};
         long long t1 = t0 + TILE;
         if (t1 > row_hi) t1 = row_hi;
         if (t0 < row_hi) fold.tile<1>(t0, t1, a, bb);
@@ -926,33 +943,30 @@ namespace {
 
 // The GEMM1-shaped blocks of an effective [KA x n_out] weight matrix M (row k multiplies A operand column k: 32
 // raw inputs, 7 new columns, the constant one) for output rows [n0, n0 + n_out) of a block that is N rows wide,
-// result scale `so` (1 for H, SO for O):
-//   ga: [N x 64 K']: K' = k hi so (meets lo), K' = 32 + k lo so / SX (meets hs)           -- raw inputs k < 32
-//   gb: [N x 32 K']: K' = k hi so / SX (meets hs)
-//   gc: [N x 16 K'] x 2: block 0 K' = c hi so (meets lo new), K' = 8 + c lo so / SX; block 1 K' = 8 + c hi so / SX
+// stored times `scale`:
+//   ga: [N x 64 K']: K' = k hi (meets lo raw and hs raw), K' = 32 + k lo (meets hs raw)                -- k < 32
+//   gc: [N x 16 K'] x 2, c = k - 32: block 0 K' = 8 + c lo (meets hs new); block 1 K' = c and 8 + c hi (meets lo new, hs new)
 struct Gemm1Writer {
-  uint16_t *ga, *gb, *gc;
+  uint16_t *ga, *gc;
   int N;
   bool overflow = false;
-  void put(const std::vector<double>& M, int n_out, int n0, float so) {
+  void put(const std::vector<double>& M, int n_out, int n0, float scale) {
     for (int k = 0; k < tc::KA; ++k)
       for (int n = 0; n < n_out; ++n) {
         const float w = (float)M[(size_t)k * n_out + n];
         float hi, lo;
         split_hi_lo(w, &hi, &lo);
-        const uint16_t h_plain = f32_to_f16(hi * so, &overflow), h_main = f32_to_f16(hi * so * tc::SX_INV, &overflow),
-                       l_main = f32_to_f16(lo * so * tc::SX_INV, &overflow);
+        const uint16_t h = f32_to_f16(hi * scale, &overflow), l = f32_to_f16(lo * scale, &overflow);
         const int row = n0 + n;
         if (k < 32) {
-          ga[kmajor_off16(N, row, k)] = h_plain;
-          ga[kmajor_off16(N, row, 32 + k)] = l_main;
-          gb[kmajor_off16(N, row, k)] = h_main;
+          ga[kmajor_off16(N, row, k)] = h;
+          ga[kmajor_off16(N, row, 32 + k)] = l;
         } else {
           const int c = k - 32;
-          gc[kmajor_off16(N, row, c)] = h_plain;
-          gc[kmajor_off16(N, row, 8 + c)] = l_main;
-          gc[(size_t)N * 16 + kmajor_off16(N, row, c)] = 0;
-          gc[(size_t)N * 16 + kmajor_off16(N, row, 8 + c)] = h_main;
+          gc[kmajor_off16(N, row, c)] = 0;
+          gc[kmajor_off16(N, row, 8 + c)] = l;
+          gc[(size_t)N * 16 + kmajor_off16(N, row, c)] = h;
+          gc[(size_t)N * 16 + kmajor_off16(N, row, 8 + c)] = h;
         }
       }
   }
@@ -991,9 +1005,9 @@ int realnvp_tc_prepare(Flow* f) {
       for (int k = l; k < 32; ++k) W0eff[(size_t)k * 128 + j] = W0[(size_t)(k - l) * 128 + j];
       for (int c = 0; c < l && c < 7; ++c) W0eff[(size_t)(32 + c) * 128 + j] = W0[(size_t)(32 - l + c) * 128 + j];
       W0eff[(size_t)39 * 128 + j] = b0[j];
-      double s = 0.0;
-      for (int k = 0; k < 39; ++k) s += fabs(W0eff[(size_t)k * 128 + j]);
-      if (s > hsum_max) hsum_max = s;
+      double sum = 0.0;
+      for (int k = 0; k < 39; ++k) sum += fabs(W0eff[(size_t)k * 128 + j]);
+      if (sum > hsum_max) hsum_max = sum;
       if (fabs((double)b0[j]) > hbias_max) hbias_max = fabs((double)b0[j]);
     }
     // V[k][n] = alpha sum_j W0eff[k][j] W2[j][n]  (+ b2[n] on the constant row)
@@ -1001,53 +1015,53 @@ int realnvp_tc_prepare(Flow* f) {
       std::vector<double> V((size_t)tc::KA * u, 0.0);
       for (int k = 0; k < tc::KA; ++k)
         for (int n = 0; n < u; ++n) {
-          double s = 0.0;
-          for (int j = 0; j < 128; ++j) s += W0eff[(size_t)k * 128 + j] * (double)W2[(size_t)j * u + n];
-          V[(size_t)k * u + n] = alpha * s + (k == 39 ? (double)b2[n] : 0.0);
+          double acc = 0.0;
+          for (int j = 0; j < 128; ++j) acc += W0eff[(size_t)k * 128 + j] * (double)W2[(size_t)j * u + n];
+          V[(size_t)k * u + n] = alpha * acc + (k == 39 ? (double)b2[n] : 0.0);
         }
       return V;
     };
     const std::vector<double> Vt = make_v(Wt, bt);
     uint8_t* base = img.data() + ch * tc::SLOT_BYTES;
+    uint8_t* gb = base + tc::SLOT_BYTES;
     {
-      Gemm1Writer wr{reinterpret_cast<uint16_t*>(base), reinterpret_cast<uint16_t*>(base + tc::SLOT_BYTES),
-                     reinterpret_cast<uint16_t*>(base + tc::SLOT_BYTES + tc::GB_MAIN_BYTES), tc::N1};
-      wr.put(W0eff, 128, 0, 1.0f);
+      Gemm1Writer wr{reinterpret_cast<uint16_t*>(base), reinterpret_cast<uint16_t*>(gb), tc::N1};
+      wr.put(W0eff, 128, 0, tc::SH);
       wr.put(scaled ? make_v(Ws, bs) : Vt, u, 128, tc::SO);
       overflow |= wr.overflow;
     }
-    // GEMM2: one K = 32 quarter = FP16 block [N2 x 96 K'] of u = beta W2 scaled by SO: K' < 32 -u_hi (meets hs - |H|),
-    // 32..63 u_lo, 64..95 u_hi (both meet hs).  Scaled layers: rows 0..31 shift, 32..63 scale, one quarter per chunk;
-    // unscaled layers: two quarters per chunk.
+    // GEMM2: one K = 32 quarter = FP16 block [N2 x 64 K'] of u = beta W2 times SU: K' < 32 u_hi (meets lo and hs),
+    // 32..63 u_lo (meets hs).  Scaled layers: rows 0..31 shift, 32..63 scale.
     const int N2 = scaled ? 64 : 32;
+    const size_t qbytes = scaled ? tc::Q64_BYTES : tc::Q32_BYTES;
     for (int q = 0; q < 4; ++q) {
-      uint16_t* c16 = reinterpret_cast<uint16_t*>(base + (size_t)(2 + (scaled ? q : (q >> 1))) * tc::SLOT_BYTES +
-                                                  ((!scaled && (q & 1)) ? tc::Q32_BYTES : 0));
+      uint8_t* qb = scaled ? base + (size_t)(2 + (q >> 1)) * tc::SLOT_BYTES + (q & 1) * qbytes
+                           : (q < 2 ? gb + 2 * tc::GB_CORR_BYTES + q * qbytes
+                                    : base + (size_t)2 * tc::SLOT_BYTES + (q & 1) * qbytes);
+      uint16_t* c16 = reinterpret_cast<uint16_t*>(qb);
       for (int kk = 0; kk < 32; ++kk)
         for (int n = 0; n < N2; ++n) {
           const int k = 32 * q + kk;
           const float v = (float)(beta * (double)((n < u) ? Wt[(size_t)k * u + n] : Ws[(size_t)k * u + (n - u)]));
           float hi, lo;
           split_hi_lo(v, &hi, &lo);
-          c16[kmajor_off16(N2, n, kk)] = f32_to_f16(-hi * tc::SO, &overflow);
-          c16[kmajor_off16(N2, n, 32 + kk)] = f32_to_f16(lo * tc::SO, &overflow);
-          c16[kmajor_off16(N2, n, 64 + kk)] = f32_to_f16(hi * tc::SO, &overflow);
+          c16[kmajor_off16(N2, n, kk)] = f32_to_f16(hi * tc::SU, &overflow);
+          c16[kmajor_off16(N2, n, 32 + kk)] = f32_to_f16(lo * tc::SU, &overflow);
         }
     }
     if (scaled) {
-      uint8_t* vt = base + (size_t)6 * tc::SLOT_BYTES;
-      Gemm1Writer wr{reinterpret_cast<uint16_t*>(vt), reinterpret_cast<uint16_t*>(vt + u * 64 * 2),
-                     reinterpret_cast<uint16_t*>(vt + u * 96 * 2), u};
+      uint8_t* vt = gb + 2 * tc::GB_CORR_BYTES;
+      Gemm1Writer wr{reinterpret_cast<uint16_t*>(vt), reinterpret_cast<uint16_t*>(vt + u * 64 * 2), u};
       wr.put(Vt, u, 0, tc::SO);
       overflow |= wr.overflow;
     }
     ch += tc::layer_chunks(scaled);
   }
   if (overflow) return HB_OK;  // a weight block leaves the half range: the CUDA-core path serves this flow
-  // range guard: hs = fp16(|H|) must stay finite (|H| <= hsum_max |x'|_max + |b0|_max), and beyond ~32 standardised
+  // range guard: hs = fp16(SH |H|) must stay finite (|H| <= hsum_max |x'|_max + |b0|_max), and beyond ~32 standardised
   // units the truncating accumulator shows (tests/test_gpu_flows.py::test_realnvp_tcgen05_large_magnitude)
   double hard = 1e30;
-  if (hsum_max > 0.0) hard = (60000.0 - hbias_max) / hsum_max;
+  if (hsum_max > 0.0) hard = (60000.0 / tc::SH - hbias_max) / hsum_max;
   if (!(hard > 1.0)) return HB_OK;
   f->tc_guard_all = (float)hard;
   f->tc_guard_raw = (float)(hard < 32.0 ? hard : 32.0);

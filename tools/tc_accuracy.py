@@ -24,8 +24,8 @@ def main():
             m.kernel_path = path
             got = np.asarray(m.predict(xs), dtype=np.float64)
             rel = np.abs(got - want) / np.abs(want)
-            print("inputs x%-4g %-9s max rel %.2e  median %.2e  max abs %.2e" % (mult, name, rel.max(), np.median(rel),
-                                                                                 np.abs(got - want).max()))
+            print("inputs x%-4g %-9s max rel %.2e  median %.2e  max abs %.2e  mean signed %.2e" % (
+                mult, name, rel.max(), np.median(rel), np.abs(got - want).max(), (got - want).mean()))
 
 
 if __name__ == "__main__":
