@@ -108,7 +108,9 @@ __host__ __device__ __forceinline__ constexpr uint32_t chunk_bytes(bool scaled, 
   return j == 0 ? GA_BYTES : j == 1 ? (scaled ? GB_S_BYTES : GB_U_BYTES) : (scaled ? 2 * Q64_BYTES : 2 * Q32_BYTES);
 }
 
-constexpr int THREADS = NT * 128 + 32 * (NT + 1);  // + producer warp + one MMA warp per tile
+constexpr int THREADS = NT * 128 + 256;  // + two warpgroups: producer warp, two MMA warps per tile, one idle warp
+constexpr int REGS_EPI = 128, REGS_AUX = 40;  // setmaxnreg: the CTA launches with 640 x 96 registers; the two auxiliary warpgroups hand back
+                                              // 2 x 128 x 56 = 14336, the three epilogue warpgroups take 3 x 128 x 32 = 12288 of them
 // shared memory carve-up (bytes)
 constexpr int SM_RING = 0;
 constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;  // per tile: the FP16 A operand (A_TILE)
@@ -119,7 +121,8 @@ constexpr int SM_TOTAL = SM_MISC + 512;
 // barrier indices (8 bytes each); per-tile barriers are indexed + tile
 constexpr int B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = B_A1FULL + NT,
               B_A2 = B_HFULL + NT /* [quarter][tile], one phase per layer */, B_OFULL = B_A2 + 4 * NT /* one phase per pass */,
-              B_OCONS = B_OFULL + NT /* O is in the epilogue's registers: one phase per pass */, B_COUNT = B_OCONS + NT;
+              B_OCONS = B_OFULL + NT /* O is in the epilogue's registers: one phase per pass */,
+              B_VT = B_OCONS + NT /* scaled layers: the x' V_shift MMAs of the second pass have completed */, B_COUNT = B_VT + NT;
 static_assert(B_COUNT * 8 <= 512 && NSLOTS <= 8, "barrier block");
 // TMEM columns (per tile: + TM_TILE * tile)
 constexpr uint32_t TM_P = 0, TM_O = 128, TM_TILE = 160;
@@ -161,6 +164,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive that hands back the barrier's state word: a value that data-depends on it cannot be computed before the arrive
+__device__ __forceinline__ uint32_t mbar_arrive_token(uint32_t bar) {
+  uint64_t st;
+  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
+  return (uint32_t)st;
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -421,7 +430,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
                   float* __restrict__ lnpred_out, FoldParams fp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NWG = NT;
-  constexpr int W_PROD = 4 * NT, W_MMA = W_PROD + 1;  // weight producer warp; the MMA warps follow
+  constexpr int W_PROD = 4 * NT, W_MMA = W_PROD + 1, W_MMB = W_MMA + NT;  // producer warp, primary and secondary MMA warps
   // lane-0 broadcast: tells the compiler the warp index (and with it the role dispatch below) is
   // warp-uniform, so the MMA warps' addresses, descriptors and loop state live on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -438,7 +447,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   const bool tr_on = blockIdx.x == 0 && lane == 0 && warp < 4;
   const int tr_s = warp;
 #else
-  const bool tr_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == W_MMA || warp == W_MMA + 1);
+  const bool tr_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == W_MMA || warp == W_MMB);
   const int tr_s = warp == 0 ? 0 : warp == 4 ? 1 : warp == W_MMA ? 2 : 3;
 #endif
 #endif
@@ -447,14 +456,16 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOTS; ++i) {
       mbar_init(BAR(B_WFULL + i), 1);
-      mbar_init(BAR(B_WEMPTY + i), NWG);  // every MMA warp releases a slot
+      mbar_init(BAR(B_WEMPTY + i), 2 * NWG);  // both MMA warps of every tile release a slot (the primary twice where
+                                              // the secondary does not read the chunk)
     }
     for (int t = 0; t < NWG; ++t) {
       mbar_init(BAR(B_A1FULL + t), 128);
       mbar_init(BAR(B_HFULL + t), 1);
       for (int q = 0; q < 4; ++q) mbar_init(BAR(B_A2 + NT * q + t), 128);
-      mbar_init(BAR(B_OFULL + t), 1);
+      mbar_init(BAR(B_OFULL + t), 2);
       mbar_init(BAR(B_OCONS + t), 128);
+      mbar_init(BAR(B_VT + t), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -474,8 +485,11 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // (setmaxnreg, first thing in every role: the epilogue warpgroups take the registers the producer / MMA warpgroups
+  // do not need)
 
   if (warp == W_PROD) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
     // ===== weight producer: the image is one batch worth of chunks, replayed every batch =====
     if (lane == 0) {
       uint32_t g = 0;
@@ -495,11 +509,18 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         }
       }
     }
-  } else if (warp >= W_MMA) {
-    // ===== MMA issuers: warp W_MMA + t serves tile t.  Each runs a straight-line program per layer with blocking
-    // mbarrier waits; the whole warp executes it (warp-uniform, so the descriptors stay in uniform registers) and
-    // one elected lane issues.  A weight slot is released when every MMA warp has committed on it.
-    const int t = warp - W_MMA;
+  } else if (warp >= W_MMA && warp < W_MMB + NT) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+    // ===== MMA issuers: tile t has a primary warp (W_MMA + t: GEMM1 and GEMM2 quarters 0, 2) and a secondary warp
+    // (W_MMB + t: quarters 1, 3) -- one warp issues a tcgen05.mma per ~49 cycles and pays ~250 cycles of fixed cost per
+    // burst (barrier check, fence, descriptors, commits); with E1 down to ~250 cycles per quarter a single issuer was
+    // what GEMM2 waited for, two alternating ones overlap their fixed costs.  Both accumulate into the same O columns
+    // (lossless: profiles/r2_issue_probe.txt).  Each runs a straight-line program per layer with
+    // blocking mbarrier waits; the whole warp executes it (warp-uniform, so the descriptors stay in uniform
+    // registers) and one elected lane issues.  A weight slot is released by 2 NT commits: one per warp that read it,
+    // two from the primary where the secondary did not.
+    const bool primary = warp < W_MMB;
+    const int t = primary ? warp - W_MMA : warp - W_MMB;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
     const uint32_t ih1 = make_idesc_f16(N1), ih32 = make_idesc_f16(32);
     const uint32_t a_h = sbase + SM_A1 + t * A_TILE;  // FP16 block: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
@@ -508,6 +529,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       mbar_wait(BAR(B_WFULL + (gidx % NSLOTS)), (gidx / NSLOTS) & 1);
     };
     auto chunk_addr = [&](uint32_t gidx) { return sbase + SM_RING + (gidx % NSLOTS) * SLOT_BYTES; };
+    auto release = [&](uint32_t gidx) { tc_commit(BAR(B_WEMPTY + (gidx % NSLOTS))); };
     // x' . B for the K = 32 raw inputs ("main"): B = the [n x 64 K'] block at ga (hi | lo).  Small terms first
     // (lo . hi, hs . lo), then the main term hs . hi
     auto issue_main = [&](uint32_t d, uint32_t ga, uint32_t n, uint32_t idesc, uint32_t acc0) {
@@ -545,27 +567,31 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       tc_fence_after();
       if (elect_one()) {
         issue_main(tb + TM_P, chunk_addr(g), N1, ih1, 0);
-        tc_commit(BAR(B_WEMPTY + (g % NSLOTS)));
+        release(g);
+        release(g);
       }
       __syncwarp();
     };
-    uint32_t g = 0, it = 0, pit = 0;
+    const int myq = primary ? 0 : 1;  // the primary issues quarters 0 and 2, the secondary 1 and 3
+    uint32_t g = 0, it = 0, pit = 0, sit = 0;
     for (int b = 0; b < P.nbatches; ++b) {
       for (int l = 0; l < nl; ++l, ++it) {
         const bool scaled = l < P.nscaled;
         const uint32_t par = it & 1;
-        // ---- GEMM1: (main, unless issued early) + correction
-        mbar_wait(BAR(B_A1FULL + t), par);
-        TR(20);
-        if (l == 0) gemm1_main(g);
-        wwait(g + 1);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_corr(tb + TM_P, chunk_addr(g + 1), N1, ih1);
-          tc_commit(BAR(B_HFULL + t));
+        if (primary) {
+          // ---- GEMM1: (main, unless issued early) + correction
+          mbar_wait(BAR(B_A1FULL + t), par);
+          TR(20);
+          if (l == 0) gemm1_main(g);
+          wwait(g + 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_corr(tb + TM_P, chunk_addr(g + 1), N1, ih1);
+            tc_commit(BAR(B_HFULL + t));
+          }
+          __syncwarp();
+          TR(21);
         }
-        __syncwarp();
-        TR(21);
         // ---- GEMM2: four K = 32 quarters, each as soon as its part of E1 has landed.  Scaled layers take the SCALE
         // rows (32..63 of each quarter block: + 4 row groups of 128 bytes) in this pass: their epilogue is the long one
         const uint32_t lbo2 = scaled ? 64u * 16u : 32u * 16u;
@@ -574,7 +600,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         auto gq = [&](int q) { return g + (scaled ? 2u : 1u) + (uint32_t)(q >> 1); };
         auto qoff = [&](int q) { return ((!scaled && q < 2) ? (uint32_t)(2 * GB_CORR_BYTES) : 0u) + (uint32_t)(q & 1) * qbytes; };
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
+        for (int q = myq; q < 4; q += 2) {
           const uint32_t gw = gq(q);
           mbar_wait(BAR(B_A2 + NT * q + t), par);
           TR(22 + q);
@@ -583,47 +609,66 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           const uint32_t wbase = chunk_addr(gw) + qoff(q) + (scaled ? 512u : 0u);
           if (elect_one()) {
             issue_quarter(q, wbase, lbo2);
-            if (q == 3) tc_commit(BAR(B_OFULL + t));
-            if (!scaled && (q & 1)) tc_commit(BAR(B_WEMPTY + (gw % NSLOTS)));
+            if (q >= 2) tc_commit(BAR(B_OFULL + t));
+            if (!scaled) release(gw);
           }
           __syncwarp();
           TR(26 + q);
         }
         if (scaled) {
           // ---- second pass: O = x' V_shift + |H| U_shift (rows 0..31 of each quarter block) once the epilogue has
-          // read the scale pre-activations out of O
+          // read the scale pre-activations out of O.  The primary's x' V_shift MMAs overwrite O: the secondary
+          // accumulates only after they have completed (B_VT)
           mbar_wait(BAR(B_OCONS + t), pit & 1);
           ++pit;
           tc_fence_after();
           TR(32);
+          if (primary) {
+            if (elect_one()) {
+              const uint32_t vt = chunk_addr(g + 1) + 2 * GB_CORR_BYTES;
+              issue_main(tb + TM_O, vt, U, ih32, 0);
+              issue_corr(tb + TM_O, vt + U * 64 * 2, U, ih32);
+              tc_commit(BAR(B_VT + t));
+            }
+            __syncwarp();
+          } else {
+            mbar_wait(BAR(B_VT + t), sit & 1);
+            tc_fence_after();
+          }
+          ++sit;
           if (elect_one()) {
-            const uint32_t vt = chunk_addr(g + 1) + 2 * GB_CORR_BYTES;
-            issue_main(tb + TM_O, vt, U, ih32, 0);
-            issue_corr(tb + TM_O, vt + U * 64 * 2, U, ih32);
 #pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
+            for (int q = myq; q < 4; q += 2) {
               issue_quarter(q, chunk_addr(gq(q)) + qoff(q), lbo2);
-              if (q & 1) tc_commit(BAR(B_WEMPTY + (gq(q) % NSLOTS)));
+              release(gq(q));
             }
             tc_commit(BAR(B_OFULL + t));
-            tc_commit(BAR(B_WEMPTY + ((g + 1) % NSLOTS)));
+            if (primary) {
+              release(g + 1);
+              release(g + 1);
+            }
           }
           __syncwarp();
           TR(33);
         }
         g += layer_chunks(scaled);
-        // ---- O is in the epilogue's registers (and with it every MMA that read P has completed): the main part of
-        // the next layer overwrites P and O under this layer's E2
-        mbar_wait(BAR(B_OCONS + t), pit & 1);
         ++pit;
-        TR(30);
-        if (l + 1 < nl) {
-          gemm1_main(g);
-          TR(31);
+        if (primary) {
+          // ---- O is in the epilogue's registers (and with it every MMA that read P has completed): the main part
+          // of the next layer overwrites P and O under this layer's E2
+          mbar_wait(BAR(B_OCONS + t), (pit - 1) & 1);
+          TR(30);
+          if (l + 1 < nl) {
+            gemm1_main(g);
+            TR(31);
+          }
         }
       }
     }
+  } else if (warp >= W_PROD) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));  // the idle warp of the second auxiliary warpgroup
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     // ===== epilogue warpgroups =====
     // Features are owned by ORIGINAL index and nothing rotates.  yt[i] = feature 32 + i,
     // x7[i] = feature i < 7 (feature i joins the transformed half from layer i + 1 on); the features that no layer
@@ -773,7 +818,11 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           tmem_ld8(tm_o + U - l, v1);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(BAR(B_OCONS + wg));
+          // ptxas schedules across asm statements: without a data dependency it sinks this arrive below the ~2 000
+          // cycles of arithmetic that follow and the second pass starts that much later.  The scale factor of the
+          // pre-activations therefore takes (runtime-zero) bits from the arrive's state word.
+          const uint32_t tok = mbar_arrive_token(BAR(B_OCONS + wg));
+          const float so_inv = __uint_as_float(__float_as_uint(SO_INV) | (tok & (uint32_t)(P.nlayers >> 16)));
           // v0 / v1 become 1 / clip(softplus(a)) in place; ldj -= sum log scale
 #pragma unroll
           for (int k0 = 0; k0 < U; k0 += 8) {
@@ -781,7 +830,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 #pragma unroll
             for (int i = k0; i < k0 + 8; ++i) {
               const bool act = i >= NX || i >= l;
-              const float a = __uint_as_float(v0[i]) * SO_INV;
+              const float a = __uint_as_float(v0[i]) * so_inv;
               float sc = softplus_clip_fast(a);
               sc = (a != a) ? a : sc;  // keep NaN (fminf/fmaxf would drop it)
               v0[i] = __float_as_uint(rcp_approx(sc));
@@ -794,7 +843,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
               if (i < l) {
-                const float a = __uint_as_float(v1[i]) * SO_INV;
+                const float a = __uint_as_float(v1[i]) * so_inv;
                 float sc = softplus_clip_fast(a);
                 sc = (a != a) ? a : sc;
                 v1[i] = __float_as_uint(rcp_approx(sc));
