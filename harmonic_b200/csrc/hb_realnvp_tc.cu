@@ -8,7 +8,7 @@
 //   3 epilogue warpgroups : each owns one tile at a time, one sample per thread (TMEM lane = sample).  A thread keeps
 //                     the 32 initially transformed features + the 7 that can enter, owned by ORIGINAL index
 //   producer warp   : streams the pre-split weight image (FP16 blocks, UMMA canonical no-swizzle K-major layout,
-//                     built once on the host) from L2 into a 7-slot ring of 20 KiB slots (3 - 4 chunks per layer) with cp.async.bulk + mbarrier
+//                     built once on the host) from L2 into an 8-slot ring of 20 KiB slots (3 - 4 chunks per layer) with cp.async.bulk + mbarrier
 //   3 MMA warps     : tcgen05.mma issuers, warp W_MMA + t serves tile t (the first also allocates TMEM); warp-uniform
 //                     straight-line program with blocking mbarrier waits, one elected lane issues.  One issuing warp
 //                     sustains one tcgen05.mma per ~49 cycles whatever N <= 64 is, while the tensor pipe itself needs
@@ -77,7 +77,7 @@ constexpr int DH = 32;        // d = conditioning width (round(D/2))
 constexpr int U = 32;         // transformed width
 constexpr int TILE = 128;
 constexpr int NT = 3;         // tiles (= epilogue warpgroups) in flight per CTA
-constexpr int NSLOTS = 7;
+constexpr int NSLOTS = 8;
 constexpr int SLOT_BYTES = 20480;
 constexpr int MAX_TC_LAYERS = 8;  // one K = 8 correction step holds 7 new columns + the constant column
 constexpr int KA = 40;            // A operand columns: 32 raw + 7 new + 1 constant
