@@ -48,6 +48,7 @@ SIGNATURES = {
     "hb_flow_destroy": (C.c_int, [C.c_void_p]),
     "hb_flow_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "hb_flow_uses_tcgen05": (C.c_int, [C.c_void_p]),
+    "hb_flow_guard_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "hb_flow_predict": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                   C.c_void_p, C.c_int, C.c_void_p]),
     "hb_flow_sample": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p,

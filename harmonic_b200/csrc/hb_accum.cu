@@ -629,6 +629,7 @@ constexpr size_t POOL_MAX = 8;
 static void accum_free(Accum* acc) {
   cudaSetDevice(acc->device);
   cudaFree(acc->packed);
+  cudaFree(acc->shadow);
   cudaFree(acc->start_dev);
   cudaFree(acc->recs);
   cudaFree(acc->gpart);

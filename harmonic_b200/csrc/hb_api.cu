@@ -136,7 +136,7 @@ static int flow_run(Flow* f, float T, const void* x, int x_dtype, long long ld, 
   if (f->desc.kind == HB_FLOW_RQSPLINE)
     return rqspline_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start, chain_lo,
                         chain_hi, a, b, st);
-  const bool tc = (f->path == HB_PATH_TCGEN05) || (f->path == HB_PATH_AUTO && f->tc_ok);
+  const bool tc = (f->path == HB_PATH_TCGEN05) || (f->path == HB_PATH_AUTO && f->tc_ok && !f->force_simt);
   if (tc)
     return realnvp_tc_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start,
                           chain_lo, chain_hi, a, b, f->tc_guard, st);
@@ -144,6 +144,30 @@ static int flow_run(Flow* f, float T, const void* x, int x_dtype, long long ld, 
                           chain_lo, chain_hi, a, b, st);
 }
 
+// Range guard of the tensor path (hb_realnvp_tc.cu): under HB_PATH_AUTO a call whose rows left the range the
+// FP16-split arithmetic serves is evaluated again on the CUDA cores (float32 FMA arithmetic, any magnitude).
+static bool guarded(const Flow* f) {
+  return f->desc.kind == HB_FLOW_REALNVP && f->path == HB_PATH_AUTO && f->tc_ok && !f->force_simt && f->tc_guard;
+}
+// rows counted since the last take; stream-ordered read + reset, then waits for the stream
+static int guard_take(Flow* f, cudaStream_t st, long long* count) {
+  unsigned long long host = 0;
+  HB_CUDA(cudaMemcpyAsync(&host, f->tc_guard, sizeof(host), cudaMemcpyDeviceToHost, st));
+  HB_CUDA(cudaStreamSynchronize(st));
+  if (host) HB_CUDA(cudaMemsetAsync(f->tc_guard, 0, sizeof(host), st));
+  *count = (long long)host;
+  return HB_OK;
+}
+struct ForceSimt {
+  Flow* f;
+  explicit ForceSimt(Flow* f_) : f(f_) { f->force_simt = true; }
+  ~ForceSimt() { f->force_simt = false; }
+};
+
+int accumulate_flow_once(Accum* acc, Flow* f, float temperature, const void* x, int x_dtype, long long ld,
+                         const void* ln_posterior, int lp_dtype, int mem, const int64_t* start_indices,
+                         long long chain_lo, long long chain_hi, long long nrows, float* lnpred_out,
+                         cudaStream_t st);
 
 static int accumulate_flow_pageable(Accum* acc, Flow* f, float temperature, const void* x, int x_dtype,
                                     long long ld, const void* lnpost, int lp_dtype,
@@ -440,6 +464,9 @@ int hb_flow_uses_tcgen05(const hb_flow* h) {
   return (f->path == HB_PATH_TCGEN05) || (f->path == HB_PATH_AUTO && f->tc_ok);
 }
 
+static int flow_predict_once(Flow* f, float temperature, const void* x, int x_dtype, int x_mem, int64_t n,
+                             int64_t ld, float* out, int out_mem, cudaStream_t st);
+
 int hb_flow_predict(hb_flow* h, float temperature, const void* x, int x_dtype, int x_mem, int64_t n,
                     int64_t ld, float* out, int out_mem, void* stream) {
   HB_REQUIRE(h != nullptr, "hb_flow_predict: NULL handle");
@@ -452,6 +479,28 @@ int hb_flow_predict(hb_flow* h, float temperature, const void* x, int x_dtype, i
   HB_REQUIRE(x != nullptr && out != nullptr, "NULL buffer");
   HB_CUDA(cudaSetDevice(f->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool guard = guarded(f);
+  int rc = flow_predict_once(f, temperature, x, x_dtype, x_mem, n, ld, out, out_mem, st);
+  if (rc || !guard) return rc;
+  long long cnt = 0;
+  rc = guard_take(f, st, &cnt);
+  if (rc || cnt == 0) return rc;
+  f->guard_rows += cnt;
+  ++f->guard_calls;
+  ForceSimt scope(f);
+  return flow_predict_once(f, temperature, x, x_dtype, x_mem, n, ld, out, out_mem, st);
+}
+
+int hb_flow_guard_stats(const hb_flow* h, int64_t* rows, int64_t* calls) {
+  HB_REQUIRE(h != nullptr, "hb_flow_guard_stats: NULL handle");
+  const Flow* f = reinterpret_cast<const Flow*>(h);
+  if (rows) *rows = f->guard_rows;
+  if (calls) *calls = f->guard_calls;
+  return HB_OK;
+}
+
+static int flow_predict_once(Flow* f, float temperature, const void* x, int x_dtype, int x_mem, int64_t n,
+                             int64_t ld, float* out, int out_mem, cudaStream_t st) {
   if (x_mem == HB_MEM_DEVICE && out_mem == HB_MEM_DEVICE)
     return flow_run(f, temperature, x, x_dtype, ld, n, nullptr, HB_F32, out, nullptr, nullptr, 0, 0,
                     0, n, st);
@@ -570,6 +619,36 @@ int hb_accumulate_flow(hb_accum* ha, hb_flow* hf, float temperature, const void*
   if (rc) return rc;
   if (!has_rows) return HB_OK;
   HB_REQUIRE(x != nullptr && ln_posterior != nullptr, "NULL input buffer");
+  if (!guarded(f))
+    return accumulate_flow_once(acc, f, temperature, x, x_dtype, ld, ln_posterior, lp_dtype, mem, start_indices,
+                                chain_lo, chain_hi, nrows, lnpred_out, st);
+  // guarded call: keep a copy of the (small) state block so that the call can be folded again on the CUDA cores
+  const size_t state_bytes = (size_t)(4 * acc->nchains + G_N) * sizeof(double);
+  if (!acc->shadow) HB_CUDA(cudaMalloc(&acc->shadow, state_bytes));
+  HB_CUDA(cudaMemcpyAsync(acc->shadow, acc->packed, state_bytes, cudaMemcpyDeviceToDevice, st));
+  rc = accumulate_flow_once(acc, f, temperature, x, x_dtype, ld, ln_posterior, lp_dtype, mem, start_indices,
+                            chain_lo, chain_hi, nrows, lnpred_out, st);
+  if (rc) return rc;
+  long long cnt = 0;
+  rc = guard_take(f, st, &cnt);
+  if (rc || cnt == 0) return rc;
+  f->guard_rows += cnt;
+  ++f->guard_calls;
+  ++acc->guard_trips;
+  HB_CUDA(cudaMemcpyAsync(acc->packed, acc->shadow, state_bytes, cudaMemcpyDeviceToDevice, st));
+  ForceSimt scope(f);
+  return accumulate_flow_once(acc, f, temperature, x, x_dtype, ld, ln_posterior, lp_dtype, mem, start_indices,
+                              chain_lo, chain_hi, nrows, lnpred_out, st);
+}
+
+}  // extern "C"
+
+namespace hb {
+int accumulate_flow_once(Accum* acc, Flow* f, float temperature, const void* x, int x_dtype, long long ld,
+                         const void* ln_posterior, int lp_dtype, int mem, const int64_t* start_indices,
+                         long long chain_lo, long long chain_hi, long long nrows, float* lnpred_out,
+                         cudaStream_t st) {
+  int rc = HB_OK;
   if (mem == HB_MEM_DEVICE)
     return flow_run(f, temperature, x, x_dtype, ld, nrows, ln_posterior, lp_dtype, lnpred_out, acc,
                     start_indices, chain_lo, chain_hi, 0, nrows, st);
@@ -618,6 +697,9 @@ int hb_accumulate_flow(hb_accum* ha, hb_flow* hf, float temperature, const void*
   HB_CUDA(cudaStreamSynchronize(st));
   return HB_OK;
 }
+}  // namespace hb
+
+extern "C" {
 
 int hb_host_alloc(size_t bytes, void** out) {
   HB_REQUIRE(out != nullptr, "hb_host_alloc: out is NULL");

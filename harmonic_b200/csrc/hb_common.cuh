@@ -318,8 +318,10 @@ struct Accum {
   // stream waits on this event
   cudaEvent_t ev_reset = nullptr;
   bool reset_pending = false;
-  // tensor-path range guard: launches of this accumulator re-run on the CUDA cores since the last reset
+  // tensor-path range guard: hb_accumulate_flow calls of this accumulator re-run on the CUDA cores since the last
+  // reset; shadow = copy of the packed block taken at the start of such a call (allocated on first use)
   long long guard_trips = 0;
+  double* shadow = nullptr;
   // finalize outputs
   double* fin = nullptr;       // device: hb_result + 4*nchains doubles
   double* fin_host = nullptr;  // pinned mirror (the 128-byte result travels alone unless arrays are asked for)

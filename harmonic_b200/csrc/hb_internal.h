@@ -130,6 +130,8 @@ struct Flow {
   // hb_flow_guard_take, and the limits on |standardised input| / |any conditioning input|
   unsigned long long* tc_guard = nullptr;
   float tc_guard_raw = 0.f, tc_guard_all = 0.f;
+  bool force_simt = false;                   // set while a guarded call is being re-run on the CUDA cores
+  long long guard_rows = 0, guard_calls = 0; // rows counted / calls re-run since creation (hb_flow_guard_stats)
 };
 
 // kernels: evaluate lnphi for rows [0, n) of x; if acc != nullptr also fold with lnpost into acc.

@@ -108,9 +108,9 @@ __host__ __device__ __forceinline__ constexpr uint32_t chunk_bytes(bool scaled, 
   return j == 0 ? GA_BYTES : j == 1 ? (scaled ? GB_S_BYTES : GB_U_BYTES) : (scaled ? 2 * Q64_BYTES : 2 * Q32_BYTES);
 }
 
-constexpr int THREADS = NT * 128 + 256;  // + two warpgroups: producer warp, two MMA warps per tile, one idle warp
-constexpr int REGS_EPI = 128, REGS_AUX = 40;  // setmaxnreg: the CTA launches with 640 x 96 registers; the two auxiliary warpgroups hand back
-                                              // 2 x 128 x 56 = 14336, the three epilogue warpgroups take 3 x 128 x 32 = 12288 of them
+constexpr int THREADS = NT * 128 + 128;  // + one auxiliary warpgroup: producer warp, one MMA warp per tile
+constexpr int REGS_EPI = 152, REGS_AUX = 40;  // setmaxnreg: the CTA launches with 512 x 128 registers; the auxiliary warpgroup hands
+                                              // back 128 x 88 = 11264, the three epilogue warpgroups take 3 x 128 x 24 = 9216 of them
 // shared memory carve-up (bytes)
 constexpr int SM_RING = 0;
 constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;  // per tile: the FP16 A operand (A_TILE)
@@ -121,8 +121,7 @@ constexpr int SM_TOTAL = SM_MISC + 512;
 // barrier indices (8 bytes each); per-tile barriers are indexed + tile
 constexpr int B_WFULL = 0, B_WEMPTY = 8, B_A1FULL = 16, B_HFULL = B_A1FULL + NT,
               B_A2 = B_HFULL + NT /* [quarter][tile], one phase per layer */, B_OFULL = B_A2 + 4 * NT /* one phase per pass */,
-              B_OCONS = B_OFULL + NT /* O is in the epilogue's registers: one phase per pass */,
-              B_VT = B_OCONS + NT /* scaled layers: the x' V_shift MMAs of the second pass have completed */, B_COUNT = B_VT + NT;
+              B_OCONS = B_OFULL + NT /* O is in the epilogue's registers: one phase per pass */, B_COUNT = B_OCONS + NT;
 static_assert(B_COUNT * 8 <= 512 && NSLOTS <= 8, "barrier block");
 // TMEM columns (per tile: + TM_TILE * tile)
 constexpr uint32_t TM_P = 0, TM_O = 128, TM_TILE = 160;
@@ -430,7 +429,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
                   float* __restrict__ lnpred_out, FoldParams fp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NWG = NT;
-  constexpr int W_PROD = 4 * NT, W_MMA = W_PROD + 1, W_MMB = W_MMA + NT;  // producer warp, primary and secondary MMA warps
+  constexpr int W_PROD = 4 * NT, W_MMA = W_PROD + 1;  // weight producer warp; the MMA warps follow
   // lane-0 broadcast: tells the compiler the warp index (and with it the role dispatch below) is
   // warp-uniform, so the MMA warps' addresses, descriptors and loop state live on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -447,7 +446,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   const bool tr_on = blockIdx.x == 0 && lane == 0 && warp < 4;
   const int tr_s = warp;
 #else
-  const bool tr_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == W_MMA || warp == W_MMB);
+  const bool tr_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == W_MMA || warp == W_MMA + 1);
   const int tr_s = warp == 0 ? 0 : warp == 4 ? 1 : warp == W_MMA ? 2 : 3;
 #endif
 #endif
@@ -456,16 +455,14 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOTS; ++i) {
       mbar_init(BAR(B_WFULL + i), 1);
-      mbar_init(BAR(B_WEMPTY + i), 2 * NWG);  // both MMA warps of every tile release a slot (the primary twice where
-                                              // the secondary does not read the chunk)
+      mbar_init(BAR(B_WEMPTY + i), NWG);  // every MMA warp releases a slot
     }
     for (int t = 0; t < NWG; ++t) {
       mbar_init(BAR(B_A1FULL + t), 128);
       mbar_init(BAR(B_HFULL + t), 1);
       for (int q = 0; q < 4; ++q) mbar_init(BAR(B_A2 + NT * q + t), 128);
-      mbar_init(BAR(B_OFULL + t), 2);
+      mbar_init(BAR(B_OFULL + t), 1);
       mbar_init(BAR(B_OCONS + t), 128);
-      mbar_init(BAR(B_VT + t), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -509,18 +506,16 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         }
       }
     }
-  } else if (warp >= W_MMA && warp < W_MMB + NT) {
+  } else if (warp >= W_MMA) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
-    // ===== MMA issuers: tile t has a primary warp (W_MMA + t: GEMM1 and GEMM2 quarters 0, 2) and a secondary warp
-    // (W_MMB + t: quarters 1, 3) -- one warp issues a tcgen05.mma per ~49 cycles and pays ~250 cycles of fixed cost per
-    // burst (barrier check, fence, descriptors, commits); with E1 down to ~250 cycles per quarter a single issuer was
-    // what GEMM2 waited for, two alternating ones overlap their fixed costs.  Both accumulate into the same O columns
-    // (lossless: profiles/r2_issue_probe.txt).  Each runs a straight-line program per layer with
-    // blocking mbarrier waits; the whole warp executes it (warp-uniform, so the descriptors stay in uniform
-    // registers) and one elected lane issues.  A weight slot is released by 2 NT commits: one per warp that read it,
-    // two from the primary where the secondary did not.
-    const bool primary = warp < W_MMB;
-    const int t = primary ? warp - W_MMA : warp - W_MMB;
+    // ===== MMA issuers: warp W_MMA + t serves tile t.  Each runs a straight-line program per layer with blocking
+    // mbarrier waits; the whole warp executes it (warp-uniform, so the descriptors stay in uniform registers) and
+    // one elected lane issues.  ONE warp issues everything that accumulates into a tile's O: MMAs of different warps
+    // are not executed in issue order (measured with two alternating issuers per tile: 10 % faster, but 3 - 20 % of
+    // the rows differed in the last bit from run to run -- the accumulator truncates, so the order of the partial
+    // sums shows), and results must not depend on scheduling.  A weight slot is released when every MMA warp has
+    // committed on it.
+    const int t = warp - W_MMA;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
     const uint32_t ih1 = make_idesc_f16(N1), ih32 = make_idesc_f16(32);
     const uint32_t a_h = sbase + SM_A1 + t * A_TILE;  // FP16 block: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
@@ -548,10 +543,8 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       mma_ss_f16(d, adn, wc, idesc, 1);
       mma_ss_f16(d, adn, wc + (uint64_t)((n * 32) >> 4), idesc, 1);
     };
-    // one GEMM2 quarter: 6 MMAs over chunk pair (2 q, 2 q + 1) of P against the quarter block at wbase (row stride lbo2)
-    auto issue_quarter = [&](int q, uint32_t wbase, uint32_t lbo2) {
-      const uint64_t bd = make_desc(wbase, lbo2, 128);
-      const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
+    // one GEMM2 quarter: 6 MMAs over chunk pair (2 q, 2 q + 1) of P against the quarter block described by bd
+    auto issue_quarter = [&](int q, uint64_t bd, uint64_t kstep2) {
       const uint32_t a0 = tb + TM_P + 32 * q;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -561,112 +554,99 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)half * kstep2, ih32, 1);
       }
     };
-    // main part of a layer's GEMM1 (chunk g = GA), released as soon as its MMAs have completed
+    // main part of a layer's GEMM1 (chunk g = GA, waited for by the caller), released as soon as its MMAs have completed
     auto gemm1_main = [&](uint32_t g) {
-      wwait(g);
       tc_fence_after();
       if (elect_one()) {
         issue_main(tb + TM_P, chunk_addr(g), N1, ih1, 0);
         release(g);
-        release(g);
       }
       __syncwarp();
     };
-    const int myq = primary ? 0 : 1;  // the primary issues quarters 0 and 2, the secondary 1 and 3
-    uint32_t g = 0, it = 0, pit = 0, sit = 0;
+    uint32_t g = 0, it = 0, pit = 0;
     for (int b = 0; b < P.nbatches; ++b) {
       for (int l = 0; l < nl; ++l, ++it) {
         const bool scaled = l < P.nscaled;
         const uint32_t par = it & 1;
-        if (primary) {
-          // ---- GEMM1: (main, unless issued early) + correction
-          mbar_wait(BAR(B_A1FULL + t), par);
-          TR(20);
-          if (l == 0) gemm1_main(g);
-          wwait(g + 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_corr(tb + TM_P, chunk_addr(g + 1), N1, ih1);
-            tc_commit(BAR(B_HFULL + t));
-          }
-          __syncwarp();
-          TR(21);
-        }
-        // ---- GEMM2: four K = 32 quarters, each as soon as its part of E1 has landed.  Scaled layers take the SCALE
-        // rows (32..63 of each quarter block: + 4 row groups of 128 bytes) in this pass: their epilogue is the long one
+        // this layer's GEMM2 operand blocks: quarter q lives in chunk gq(q) at offset qoff(q); the descriptors are
+        // formed here, off the per-quarter path.  Scaled layers take the SCALE rows (32..63 of each quarter block:
+        // + 4 row groups of 128 bytes) in the first pass: their epilogue is the long one
         const uint32_t lbo2 = scaled ? 64u * 16u : 32u * 16u;
         const uint32_t qbytes = scaled ? (uint32_t)Q64_BYTES : (uint32_t)Q32_BYTES;
-        // quarter q lives in chunk gq(q) at offset qoff(q)
+        const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
         auto gq = [&](int q) { return g + (scaled ? 2u : 1u) + (uint32_t)(q >> 1); };
         auto qoff = [&](int q) { return ((!scaled && q < 2) ? (uint32_t)(2 * GB_CORR_BYTES) : 0u) + (uint32_t)(q & 1) * qbytes; };
-#pragma unroll 1
-        for (int q = myq; q < 4; q += 2) {
-          const uint32_t gw = gq(q);
+        uint64_t bd[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bd[q] = make_desc(chunk_addr(gq(q)) + qoff(q), lbo2, 128);
+        const uint64_t pass1 = scaled ? (uint64_t)(512 >> 4) : 0ull;
+        // ---- GEMM1: (main, unless issued early) + correction
+        if (l > 0) wwait(g + 1);  // (idle anyway: the chunk checks come ahead of the epilogue's signals)
+        mbar_wait(BAR(B_A1FULL + t), par);
+        TR(20);
+        if (l == 0) {
+          wwait(g);
+          gemm1_main(g);
+          wwait(g + 1);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          issue_corr(tb + TM_P, chunk_addr(g + 1), N1, ih1);
+          tc_commit(BAR(B_HFULL + t));
+        }
+        __syncwarp();
+        TR(21);
+        // ---- GEMM2: four K = 32 quarters, each as soon as its part of E1 has landed
+        if (scaled) wwait(g + 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q == 2) wwait(gq(2));
           mbar_wait(BAR(B_A2 + NT * q + t), par);
           TR(22 + q);
-          wwait(gw);
           tc_fence_after();
-          const uint32_t wbase = chunk_addr(gw) + qoff(q) + (scaled ? 512u : 0u);
           if (elect_one()) {
-            issue_quarter(q, wbase, lbo2);
-            if (q >= 2) tc_commit(BAR(B_OFULL + t));
-            if (!scaled) release(gw);
+            issue_quarter(q, bd[q] + pass1, kstep2);
+            if (q == 3) tc_commit(BAR(B_OFULL + t));
+            if (!scaled && (q & 1)) release(gq(q));
           }
           __syncwarp();
           TR(26 + q);
         }
         if (scaled) {
           // ---- second pass: O = x' V_shift + |H| U_shift (rows 0..31 of each quarter block) once the epilogue has
-          // read the scale pre-activations out of O.  The primary's x' V_shift MMAs overwrite O: the secondary
-          // accumulates only after they have completed (B_VT)
+          // read the scale pre-activations out of O
           mbar_wait(BAR(B_OCONS + t), pit & 1);
           ++pit;
           tc_fence_after();
           TR(32);
-          if (primary) {
-            if (elect_one()) {
-              const uint32_t vt = chunk_addr(g + 1) + 2 * GB_CORR_BYTES;
-              issue_main(tb + TM_O, vt, U, ih32, 0);
-              issue_corr(tb + TM_O, vt + U * 64 * 2, U, ih32);
-              tc_commit(BAR(B_VT + t));
-            }
-            __syncwarp();
-          } else {
-            mbar_wait(BAR(B_VT + t), sit & 1);
-            tc_fence_after();
-          }
-          ++sit;
           if (elect_one()) {
-#pragma unroll 1
-            for (int q = myq; q < 4; q += 2) {
-              issue_quarter(q, chunk_addr(gq(q)) + qoff(q), lbo2);
-              release(gq(q));
+            const uint32_t vt = chunk_addr(g + 1) + 2 * GB_CORR_BYTES;
+            issue_main(tb + TM_O, vt, U, ih32, 0);
+            issue_corr(tb + TM_O, vt + U * 64 * 2, U, ih32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              issue_quarter(q, bd[q], kstep2);
+              if (q & 1) release(gq(q));
             }
             tc_commit(BAR(B_OFULL + t));
-            if (primary) {
-              release(g + 1);
-              release(g + 1);
-            }
+            release(g + 1);
           }
           __syncwarp();
           TR(33);
         }
         g += layer_chunks(scaled);
+        // ---- O is in the epilogue's registers (and with it every MMA that read P has completed): the main part of
+        // the next layer overwrites P and O under this layer's E2
+        if (l + 1 < nl) wwait(g);
+        mbar_wait(BAR(B_OCONS + t), pit & 1);
         ++pit;
-        if (primary) {
-          // ---- O is in the epilogue's registers (and with it every MMA that read P has completed): the main part
-          // of the next layer overwrites P and O under this layer's E2
-          mbar_wait(BAR(B_OCONS + t), (pit - 1) & 1);
-          TR(30);
-          if (l + 1 < nl) {
-            gemm1_main(g);
-            TR(31);
-          }
+        TR(30);
+        if (l + 1 < nl) {
+          gemm1_main(g);
+          TR(31);
         }
       }
     }
-  } else if (warp >= W_PROD) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));  // the idle warp of the second auxiliary warpgroup
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     // ===== epilogue warpgroups =====

@@ -159,7 +159,22 @@ class FlowModel(Model):
                 lib.hb_flow_destroy(h)
                 raise
         self._handle, self._handle_key = h, key
+        self._guard_rows = self._guard_calls = 0
         return h
+
+    def _warn_guard(self, h):
+        """The tensor path's range guard (include/harmonic_b200.h, hb_flow_guard_stats): say so when a call was
+        evaluated again on the CUDA cores because samples lay outside the range the FP16-split arithmetic serves."""
+        if self.kernel_path != _lib.HB_PATH_AUTO:
+            return
+        rows, calls = _lib.C.c_int64(0), _lib.C.c_int64(0)
+        _lib.check(_lib.load().hb_flow_guard_stats(h, _lib.C.byref(rows), _lib.C.byref(calls)))
+        if calls.value > self._guard_calls:
+            from . import logs
+            logs.warning_log(
+                "harmonic_b200: %d sample rows outside the tensor-core path's range; the call was evaluated on the "
+                "CUDA cores (float32 FMA arithmetic) instead." % (rows.value - self._guard_rows))
+        self._guard_rows, self._guard_calls = rows.value, calls.value
 
     def _release(self):
         if getattr(self, "_handle", None) is not None:
@@ -207,6 +222,7 @@ class FlowModel(Model):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(lib.hb_flow_predict(h, self.temperature, ref.ptr, ref.dtype, _lib.HB_MEM_DEVICE,
                                            ref.shape[0], ref.ld, out.data_ptr(), _lib.HB_MEM_DEVICE, stream))
+            self._warn_guard(h)
             return out[0] if one_d else out
         xa = np.asarray(x)
         one_d = xa.ndim == 1
@@ -219,6 +235,7 @@ class FlowModel(Model):
         h = self._get_handle()
         _lib.check(lib.hb_flow_predict(h, self.temperature, ref.ptr, ref.dtype, _lib.HB_MEM_HOST,
                                        ref.shape[0], ref.ld, out.ctypes.data, _lib.HB_MEM_HOST, None))
+        self._warn_guard(h)
         return out[0] if one_d else out
 
     # ------------------------------------------------------------------ harmonic/model.py:239-275

@@ -100,7 +100,7 @@ typedef struct {
   double lnpredictmax, lnpredictmin; /* harmonic/evidence.py:351-352 */
   double nsamples_total;
   double mean_nsamples_eff; /* mean over chains of nsamples_eff_per_chain (harmonic/evidence.py:372-378) */
-  double guard_trips;       /* tensor-path range guard: launches re-run on the CUDA cores since the last reset */
+  double guard_trips;       /* tensor-path range guard: hb_accumulate_flow calls re-run on the CUDA cores since the last reset */
   double reserved;
 } hb_result;
 
@@ -120,6 +120,12 @@ int hb_flow_destroy(hb_flow* flow);
 int hb_flow_set_path(hb_flow* flow, int path);
 /* 1 if the tcgen05 path will be used for this flow */
 int hb_flow_uses_tcgen05(const hb_flow* flow);
+/* Range guard of the tcgen05 path under HB_PATH_AUTO: sample rows found outside the range its FP16-split arithmetic
+ * serves (|standardised input| > 32, or a hidden pre-activation that would leave the half range) since the flow was
+ * created, and the hb_flow_predict / hb_accumulate_flow calls that were therefore evaluated again on the CUDA-core
+ * path (float32 FMA arithmetic, as harmonic/flows.py:159-180 runs it on XLA's float32).  With HB_PATH_TCGEN05 forced
+ * nothing is re-run. */
+int hb_flow_guard_stats(const hb_flow* flow, int64_t* rows, int64_t* calls);
 
 /* Replaces FlowModel.predict (harmonic/model.py:196-237): out[i] = ln phi(x_i) at `temperature`
  * (0 < T <= 1 is validated by the caller, as the reference does on every call). */

@@ -174,31 +174,68 @@ def test_realnvp_tcgen05_layers_nan(layers):
     assert np.isnan(got[11]) and np.isnan(got[12])
 
 
-@pytest.mark.parametrize("scale,mult", [(5.0, 1.0), (30.0, 8.0), (300.0, None), (3e4, None)])
-def test_realnvp_tcgen05_large_magnitude(scale, mult):
+@pytest.mark.parametrize("scale,trips", [(2.0, False), (5.0, None), (30.0, True), (300.0, True), (3e4, True)])
+def test_realnvp_tcgen05_large_magnitude(scale, trips):
     """Inputs far outside the trained range: the scaled layers hit the 1e-3 clip, which multiplies every
-    float32 rounding error by up to 1e3 per layer.  Up to 30x the trained range the tensor-core path must stay
-    inside the conditioning-aware bound of check_predict, widened 8x where the flow is this ill-conditioned: the
-    tensor cores truncate their float32 accumulator on every MMA step (profiles/r1_tensor_accum_rounding.txt),
-    about 3-6x the error of a float32 FMA chain over the accumulation steps of one coupling layer.
-    At 300x and beyond, hidden activations pass 65504 * 2^11 = 1.3e8 and the FP16 operands of GEMM2 saturate: the
-    documented limit of the tensor path (HB_PATH_SIMT is exact float32 at any magnitude).  There the
-    results must stay finite and within a few per cent, and the bulk of the samples accurate."""
+    float32 rounding error by up to 1e3 per layer, the tensor cores truncate their float32 accumulator on every MMA
+    step (profiles/r1_tensor_accum_rounding.txt) and beyond |hidden| = 2047 the FP16 operands of GEMM2 would overflow.
+    HB_PATH_AUTO therefore guards the tensor path: rows with a standardised input beyond 32 (or a hidden unit that
+    could leave the half range) are counted by the kernel and the call is evaluated again on the CUDA cores, so AUTO
+    meets the SAME bound as the float32 path at every magnitude (no extra slack) and equals it bit for bit whenever
+    the guard trips.  At 2x the trained range nothing trips and the tensor path itself meets the bound; at 5x a few
+    rows whose transformed features were blown up by a clipped scale (1 / 1e-3) trip it."""
     m = util.make_realnvp(64, seed=5, standardize=True, ws=0.3)
-    m.kernel_path = _lib.HB_PATH_TCGEN05
+    assert m.kernel_path == _lib.HB_PATH_AUTO
+    lib = _lib.load()
+    assert lib.hb_flow_uses_tcgen05(m._get_handle()) == 1
     x = (samples(4000, 64, seed=16) * scale).astype(np.float32)
+    rows, calls = _lib.C.c_int64(0), _lib.C.c_int64(0)
     got = m.predict(x)
+    _lib.check(lib.hb_flow_guard_stats(m._get_handle(), _lib.C.byref(rows), _lib.C.byref(calls)))
+    if trips is not None:
+        assert (calls.value == 1 and rows.value > 0) if trips else (calls.value == 0 and rows.value == 0)
+    trips = calls.value > 0
     assert np.isfinite(got).all()
-    if mult is None:
-        want = util.oracle_predict(m, x)
-        rel = np.abs(got - want) / np.abs(want)
-        assert rel.max() < 1e-1
-        assert np.median(rel) < (1e-5 if scale <= 300.0 else 5e-3)
-        if scale <= 300.0:
-            m.kernel_path = _lib.HB_PATH_SIMT  # the CUDA-core path has no such limit
-            util.check_predict(m, x, m.predict(x), slack_mult=2.0)
-    else:
-        util.check_predict(m, x, got, slack_mult=mult)
+    m2 = util.make_realnvp(64, seed=5, standardize=True, ws=0.3)
+    m2.kernel_path = _lib.HB_PATH_SIMT
+    simt = m2.predict(x)
+    if trips:
+        np.testing.assert_array_equal(got, simt)
+    if scale <= 30.0:
+        util.check_predict(m, x, got)  # slack_mult = 1
+    elif scale <= 300.0:
+        util.check_predict(m, x, got, slack_mult=2.0)  # the float32 path's own bound at this magnitude
+    # the device-resident path takes the same route
+    import torch
+    got_dev = m.predict(torch.from_numpy(x).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(got_dev, got)
+
+
+def test_realnvp_tcgen05_guard_in_add_chains(caplog):
+    """One chain of a set has samples tens of sigmas out: under AUTO the whole add_chains call is folded again on the
+    CUDA cores (state restored from the copy taken at the start of the call), a second, in-range call then stays on
+    the tensor path; the result equals the float32 path's and matches the oracle."""
+    import logging
+    m = util.make_realnvp(64, seed=9, standardize=True, ws=0.3)
+    ch_ok = util.gaussian_chains(64, 12, 700, seed=3, ragged=True)
+    ch_far = util.gaussian_chains(64, 12, 500, seed=4, ragged=True)
+    ch_far.samples[37, 5] = 150.0
+    ev = hm.Evidence(12, m)
+    with caplog.at_level(logging.WARNING, logger="Harmonic"):
+        ev.add_chains(ch_far)
+    assert ev.guard_trips == 1 and any("CUDA cores" in r.message for r in caplog.records)
+    ev.add_chains(ch_ok)
+    assert ev.guard_trips == 1
+    m2 = util.make_realnvp(64, seed=9, standardize=True, ws=0.3)
+    m2.kernel_path = _lib.HB_PATH_SIMT
+    ev2 = hm.Evidence(12, m2)
+    ev2.add_chains(ch_far)
+    ev2.add_chains(ch_ok)
+    assert abs(ev.ln_evidence_inv - ev2.ln_evidence_inv) < 1e-6
+    ref = util.oracle_evidence(m, ch_far)
+    ev3 = hm.Evidence(12, m)
+    ev3.add_chains(ch_far)
+    util.assert_evidence_close(ev3, ref)
 
 
 def test_realnvp_tcgen05_fused_vs_oracle_and_auto_path():
