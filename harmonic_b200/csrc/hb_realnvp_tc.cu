@@ -109,8 +109,8 @@ __host__ __device__ __forceinline__ constexpr uint32_t chunk_bytes(bool scaled, 
 }
 
 constexpr int THREADS = NT * 128 + 128;  // + one auxiliary warpgroup: producer warp, one MMA warp per tile
-constexpr int REGS_EPI = 152, REGS_AUX = 40;  // setmaxnreg: the CTA launches with 512 x 128 registers; the auxiliary warpgroup hands
-                                              // back 128 x 88 = 11264, the three epilogue warpgroups take 3 x 128 x 24 = 9216 of them
+constexpr int REGS_EPI = 160, REGS_AUX = 32;  // setmaxnreg: the CTA launches with 512 x 128 registers; the auxiliary warpgroup hands
+                                              // back 128 x 96 = 12288, the three epilogue warpgroups take 3 x 128 x 32 = all of them
 // shared memory carve-up (bytes)
 constexpr int SM_RING = 0;
 constexpr int SM_A1 = SM_RING + NSLOTS * SLOT_BYTES;  // per tile: the FP16 A operand (A_TILE)
@@ -676,6 +676,13 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
     uint32_t it = 0, pit = 0;
     unsigned int nguard = 0;
 
+    // The conditioning half of a tile's rows -- all the A operand needs -- is fetched into registers under the last
+    // layer of the tile before (xpre); the transformed half is loaded under GEMM1 of layer 0.
+    float xpre[DH];
+    {
+      const long long r0 = row_lo + tid;
+      load_half<XT>(x + (r0 < row_hi ? r0 : 0) * ld, xpre);
+    }
     for (int b = 0; b < P.nbatches; ++b) {
       const long long t0 = row_lo + (long long)b * TILE;
       const long long r = t0 + tid;
@@ -687,11 +694,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
       float lp = 0.f;
       if (FOLD) lp = live ? (float)lnpost[r] : 0.f;  // in flight until the fold at the end of the tile
       {
-        // conditioning half first: it is all the A operand needs; the transformed half is loaded under GEMM1 of layer 0
         float y[DH];
-        load_half<XT>(xrow, y);
 #pragma unroll
-        for (int i = 0; i < DH; ++i) y[i] = fmaf(y[i], pre_s[i], pre_s[D + i]);
+        for (int i = 0; i < DH; ++i) y[i] = fmaf(xpre[i], pre_s[i], pre_s[D + i]);
         // A operand, written once per tile: chunk c = columns 8 c .. 8 c + 7 (lo), chunk 4 + c the same columns (hs)
 #pragma unroll
         for (int c = 0; c < DH / 8; ++c) {
@@ -766,6 +771,10 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         if (l == 0) {
 #pragma unroll
           for (int i = 0; i < U; ++i) yt[i] = fmaf(yt[i], pre_s[DH + i], pre_s[D + DH + i]);
+        }
+        if (l == nl - 1 && b + 1 < P.nbatches) {  // next tile's conditioning half: in flight under this layer's E2 and the fold
+          const long long rn = r + TILE;
+          load_half<XT>(x + (rn < row_hi ? rn : 0) * ld, xpre);
         }
         // ---- E2
         mbar_wait(BAR(B_OFULL + wg), pit & 1);
