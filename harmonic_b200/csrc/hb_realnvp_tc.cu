@@ -22,7 +22,7 @@
 // no bias, nothing but conversions -- which is what the kernel's issue slots go to (profiles/r2_alu_probe.txt).
 //
 // Per coupling layer and tile
-//   GEMM1  [H | O] [128 x 160] = [x(0..31) | new(0..6) | 1] . [W0' | V]     A, B from shared memory, K = 40
+//   GEMM1  [H | O] [128 x 160] = [32 input slots | newest column | 1] . [W0' | V]   A, B from shared memory, 7 MMAs
 //   E1     |H| -> FP16 pair (hs, |H| - hs), in place of H                    eight 16-column chunks, loads prefetched
 //   GEMM2  O[128 x 32] += |H|[:, quarter] . U[quarter, :]                    A from TMEM, 6 FP16 MMAs per K = 32 quarter
 //   E2     y -= O (shift) or softplus-clip scale epilogue on y, log-det
@@ -49,11 +49,13 @@
 // GEMM1 without re-staging activations.  The flow permutes by one position per layer
 // (harmonic/flows.py:65-66), so layer l conditions on ORIGINAL features l .. l+31: the features below
 // 32 are still the raw (standardised) inputs, and the j < l features 32+j were frozen by layer j's
-// epilogue.  The A operand is therefore written ONCE per tile -- the raw x(0..31) -- plus one new
-// column per layer; each layer's [W0' | V] is stored shifted by l rows ("main", K = 32) next to a K = 8
-// "correction" block whose rows multiply the new columns and a constant-one column that carries the
-// biases.  The main part of layer l+1 is issued as soon as layer l's epilogue has read O,
-// i.e. it runs under layer l's epilogue; only the 2-MMA correction waits for the new column.
+// epilogue.  The A operand is therefore written ONCE per tile -- the raw x(0..31) in 32 input slots -- plus one
+// new column per layer: layer l's epilogue writes feature 32 + l into the K' = 16 "correction" operand
+// [lo, hs, hs, 1, 1, 0 ...] (met by ONE MMA against [hi, hi, lo of its weights; hi, lo of the bias]) and into input
+// slot l, which no later layer reads as a raw input, where the layers after the next find it.  Each layer's
+// [W0' | V] is stored accordingly ("main", K = 32: 6 MMAs).  The main part of layer l+1 is issued as soon as layer
+// l's epilogue has read O, i.e. it runs under layer l's epilogue -- slot l is being overwritten at that time and
+// carries zero weights in layer l+1 --; only the 1-MMA correction waits for the new column.
 //
 // GEMM2 is pipelined with E1 at quarter granularity: quarter q's operands replace its own 32 H columns, its
 // GEMM2 step runs while the epilogue computes quarter q + 1 (one mbarrier per quarter: the epilogue may run a
@@ -79,9 +81,9 @@ constexpr int TILE = 128;
 constexpr int NT = 3;         // tiles (= epilogue warpgroups) in flight per CTA
 constexpr int NSLOTS = 8;
 constexpr int SLOT_BYTES = 20480;
-constexpr int MAX_TC_LAYERS = 8;  // one K = 8 correction step holds 7 new columns + the constant column
-constexpr int KA = 40;            // A operand columns: 32 raw + 7 new + 1 constant
-constexpr int A_TILE = KA / 4 * 2048;  // FP16 block, 10 chunks of 8 columns: lo raw 0-3 | hs raw 4-7 | lo new 8 | hs new 9
+constexpr int MAX_TC_LAYERS = 8;  // the epilogue keeps 7 features that can enter the transformed half in registers
+constexpr int KA = 34;            // rows of a layer's effective GEMM1 weight matrix: 32 input slots, the newest column, the constant
+constexpr int A_TILE = 10 * 2048;     // FP16 block, 10 chunks of 8 columns: lo 0-3 | hs 4-7 | correction operand 8 | zero 9
 constexpr int N1 = 128 + U;       // GEMM1 output columns: H | O
 constexpr float SH = 32.0f;                        // H accumulates SH times its value (so that w_lo is a normal half)
 constexpr float SU = 32.0f;                        // GEMM2 weights travel times SU (u_lo a normal half)
@@ -90,8 +92,9 @@ constexpr double LEAKY_SLOPE = 0.01;
 
 // weight image, per layer (FP16 blocks, hi = the 11 leading bits of a weight, lo = the rest; ONE hi block serves
 // both halves of an activation's split):
-//   chunk 0  GA   [160 x 64 K']: K' < 32 hi (meets lo raw AND hs raw), K' >= 32 lo (meets hs raw)
-//   chunk 1  GB   corrections [160 x 16 K'] x 2 over [lo new | hs new]: [0 ; lo], then [hi ; hi];
+//   chunk 0  GA   [160 x 64 K']: K' < 32 hi (meets lo AND hs of the 32 input slots), K' >= 32 lo (meets hs)
+//   chunk 1  GB   correction [160 x 16 K'] over [lo new, hs new, hs new, 1, 1, 0 ...]: hi, hi, lo of the newest
+//                 column's weights, hi, lo of the bias;
 //                 then unscaled layers: GEMM2 quarters 0, 1; scaled layers: VT = the GEMM1 blocks of V_shift (N = 32)
 //   chunk 2, (3)  GEMM2 quarters 2, 3 (unscaled) / 0, 1 and 2, 3 (scaled)
 //   a GEMM2 quarter (K = 32 hidden units) is [N2 x 64 K']: K' < 32 hi (meets hs - and lo), K' >= 32 lo (meets hs);
@@ -100,8 +103,8 @@ constexpr int GA_BYTES = N1 * 64 * 2;
 constexpr int GB_CORR_BYTES = N1 * 16 * 2;     // one correction block
 constexpr int Q32_BYTES = 32 * 64 * 2;
 constexpr int Q64_BYTES = 64 * 64 * 2;
-constexpr int VT_BYTES = U * (64 + 16 + 16) * 2;
-constexpr int GB_U_BYTES = 2 * GB_CORR_BYTES + 2 * Q32_BYTES, GB_S_BYTES = 2 * GB_CORR_BYTES + VT_BYTES;
+constexpr int VT_BYTES = U * (64 + 16) * 2;
+constexpr int GB_U_BYTES = GB_CORR_BYTES + 2 * Q32_BYTES, GB_S_BYTES = GB_CORR_BYTES + VT_BYTES;
 static_assert(GA_BYTES <= SLOT_BYTES && GB_U_BYTES <= SLOT_BYTES && GB_S_BYTES <= SLOT_BYTES && 2 * Q64_BYTES <= SLOT_BYTES, "slot");
 __host__ __device__ __forceinline__ constexpr int layer_chunks(bool scaled) { return scaled ? 4 : 3; }
 __host__ __device__ __forceinline__ constexpr uint32_t chunk_bytes(bool scaled, int j) {
@@ -537,11 +540,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 #pragma unroll
       for (int k = 0; k < 2; ++k) mma_ss_f16(d, adx + (uint64_t)((2 + k) * 256), wh + (uint64_t)k * kstep, idesc, 1);
     };
-    // the K = 8 new / constant columns ("corr"): K' = 16 each over A = [lo new | hs new]: B = [0 ; lo], then [hi ; hi]
+    // the newest column and the constant ("corr"): ONE K' = 16 MMA over A = [lo new, hs new, hs new, 1, 1, 0 ...]
     auto issue_corr = [&](uint32_t d, uint32_t gc, uint32_t n, uint32_t idesc) {
-      const uint64_t wc = make_desc(gc, n * 16, 128);
-      mma_ss_f16(d, adn, wc, idesc, 1);
-      mma_ss_f16(d, adn, wc + (uint64_t)((n * 32) >> 4), idesc, 1);
+      mma_ss_f16(d, adn, make_desc(gc, n * 16, 128), idesc, 1);
     };
     // one GEMM2 quarter: 6 MMAs over chunk pair (2 q, 2 q + 1) of P against the quarter block described by bd
     auto issue_quarter = [&](int q, uint64_t bd, uint64_t kstep2) {
@@ -575,7 +576,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         const uint32_t qbytes = scaled ? (uint32_t)Q64_BYTES : (uint32_t)Q32_BYTES;
         const uint64_t kstep2 = (uint64_t)((2 * lbo2) >> 4);
         auto gq = [&](int q) { return g + (scaled ? 2u : 1u) + (uint32_t)(q >> 1); };
-        auto qoff = [&](int q) { return ((!scaled && q < 2) ? (uint32_t)(2 * GB_CORR_BYTES) : 0u) + (uint32_t)(q & 1) * qbytes; };
+        auto qoff = [&](int q) { return ((!scaled && q < 2) ? (uint32_t)GB_CORR_BYTES : 0u) + (uint32_t)(q & 1) * qbytes; };
         uint64_t bd[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) bd[q] = make_desc(chunk_addr(gq(q)) + qoff(q), lbo2, 128);
@@ -620,7 +621,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           tc_fence_after();
           TR(32);
           if (elect_one()) {
-            const uint32_t vt = chunk_addr(g + 1) + 2 * GB_CORR_BYTES;
+            const uint32_t vt = chunk_addr(g + 1) + GB_CORR_BYTES;
             issue_main(tb + TM_O, vt, U, ih32, 0);
             issue_corr(tb + TM_O, vt + U * 64 * 2, U, ih32);
 #pragma unroll
@@ -713,10 +714,9 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           *reinterpret_cast<uint4*>(a1 + (4 + c) * 2048 + tid * 16) = phi;
         }
         {
-          // new columns: none yet; the constant-one column (the 8th) is hs = fp16(1) = 0x3C00, lo = 0
-          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = z;
-          *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0x3C000000u);
+          // correction operand [lo new, hs new, hs new, 1, 1, 0, 0, 0 | 0 x 8]: no new column yet
+          *reinterpret_cast<uint4*>(a1 + 8 * 2048 + tid * 16) = make_uint4(0u, 0x3C000000u, 0x00003C00u, 0u);
+          *reinterpret_cast<uint4*>(a1 + 9 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) x7[i] = y[i];
@@ -875,9 +875,12 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
 #pragma unroll
           for (int i = 1; i < NX; ++i) v = (l == i) ? yt[i] : v;
           gnew = fmaxf(gnew, fabsf(v));
-          const uint16_t hs16 = to_f16(v);
-          *reinterpret_cast<uint16_t*>(a1 + 8 * 2048 + tid * 16 + l * 2) = to_f16(v - from_f16(hs16));
-          *reinterpret_cast<uint16_t*>(a1 + 9 * 2048 + tid * 16 + l * 2) = hs16;
+          // the next layer meets it in the correction operand; the layers after that in input slot l (dead as a raw
+          // input from layer l + 1 on; the next layer's main MMAs, already in flight, meet that slot with zero weights)
+          const uint32_t hs16 = to_f16(v), lo16 = to_f16(v - from_f16((uint16_t)hs16));
+          *reinterpret_cast<uint2*>(a1 + 8 * 2048 + tid * 16) = make_uint2(lo16 | (hs16 << 16), hs16 | 0x3C000000u);
+          *reinterpret_cast<uint16_t*>(a1 + tid * 16 + l * 2) = (uint16_t)lo16;
+          *reinterpret_cast<uint16_t*>(a1 + 4 * 2048 + tid * 16 + l * 2) = (uint16_t)hs16;
         }
         TR(10);
       }
@@ -979,11 +982,12 @@ static inline uint16_t f32_to_f16(float f, bool* overflow) {
 
 namespace {
 
-// The GEMM1-shaped blocks of an effective [KA x n_out] weight matrix M (row k multiplies A operand column k: 32
-// raw inputs, 7 new columns, the constant one) for output rows [n0, n0 + n_out) of a block that is N rows wide,
-// stored times `scale`:
-//   ga: [N x 64 K']: K' = k hi (meets lo raw and hs raw), K' = 32 + k lo (meets hs raw)                -- k < 32
-//   gc: [N x 16 K'] x 2, c = k - 32: block 0 K' = 8 + c lo (meets hs new); block 1 K' = c and 8 + c hi (meets lo new, hs new)
+// The GEMM1-shaped blocks of an effective [KA x n_out] weight matrix M (rows 0..31 multiply the 32 input slots of the
+// A operand, row 32 the newest column, row 33 the constant one) for output rows [n0, n0 + n_out) of a block that is N
+// rows wide, stored times `scale`:
+//   ga: [N x 64 K']: K' = k hi (meets lo and hs of slot k), K' = 32 + k lo (meets hs)
+//   gc: [N x 16 K']: K' = 0, 1 hi and 2 lo of the newest column's row (meet lo new, hs new, hs new), 3 hi and 4 lo of
+//       the constant row (meet the two ones)
 struct Gemm1Writer {
   uint16_t *ga, *gc;
   int N;
@@ -999,12 +1003,13 @@ struct Gemm1Writer {
         if (k < 32) {
           ga[kmajor_off16(N, row, k)] = h;
           ga[kmajor_off16(N, row, 32 + k)] = l;
+        } else if (k == 32) {
+          gc[kmajor_off16(N, row, 0)] = h;
+          gc[kmajor_off16(N, row, 1)] = h;
+          gc[kmajor_off16(N, row, 2)] = l;
         } else {
-          const int c = k - 32;
-          gc[kmajor_off16(N, row, c)] = 0;
-          gc[kmajor_off16(N, row, 8 + c)] = l;
-          gc[(size_t)N * 16 + kmajor_off16(N, row, c)] = h;
-          gc[(size_t)N * 16 + kmajor_off16(N, row, 8 + c)] = h;
+          gc[kmajor_off16(N, row, 3)] = h;
+          gc[kmajor_off16(N, row, 4)] = l;
         }
       }
   }
@@ -1036,15 +1041,17 @@ int realnvp_tc_prepare(Flow* f) {
     const float* bt = Wt + (size_t)128 * u;
     const float* Ws = bt + u;
     const float* bs = Ws + (size_t)128 * u;
-    // W0eff[k][j]: A column k (original feature k < 32; new column c = k - 32 = frozen feature 32 + c; constant) meets
-    // W0 row k - l (zero for k < l) / row 32 - l + c (c < l) / b0
+    // W0eff[k][j]: input slot k < 32 holds original feature k for k >= l (W0 row k - l) and the frozen feature 32 + k
+    // for k < l - 1 (W0 row 32 - l + k); slot l - 1 is being overwritten while this layer's main MMAs run and gets
+    // zero weights -- its feature, the newest column, is row 32 (W0 row 31); row 33 is b0
     std::vector<double> W0eff((size_t)tc::KA * 128, 0.0);
     for (int j = 0; j < 128; ++j) {
       for (int k = l; k < 32; ++k) W0eff[(size_t)k * 128 + j] = W0[(size_t)(k - l) * 128 + j];
-      for (int c = 0; c < l && c < 7; ++c) W0eff[(size_t)(32 + c) * 128 + j] = W0[(size_t)(32 - l + c) * 128 + j];
-      W0eff[(size_t)39 * 128 + j] = b0[j];
+      for (int k = 0; k + 1 < l; ++k) W0eff[(size_t)k * 128 + j] = W0[(size_t)(32 - l + k) * 128 + j];
+      if (l > 0) W0eff[(size_t)32 * 128 + j] = W0[(size_t)31 * 128 + j];
+      W0eff[(size_t)33 * 128 + j] = b0[j];
       double sum = 0.0;
-      for (int k = 0; k < 39; ++k) sum += fabs(W0eff[(size_t)k * 128 + j]);
+      for (int k = 0; k < 33; ++k) sum += fabs(W0eff[(size_t)k * 128 + j]);
       if (sum > hsum_max) hsum_max = sum;
       if (fabs((double)b0[j]) > hbias_max) hbias_max = fabs((double)b0[j]);
     }
@@ -1055,7 +1062,7 @@ int realnvp_tc_prepare(Flow* f) {
         for (int n = 0; n < u; ++n) {
           double acc = 0.0;
           for (int j = 0; j < 128; ++j) acc += W0eff[(size_t)k * 128 + j] * (double)W2[(size_t)j * u + n];
-          V[(size_t)k * u + n] = alpha * acc + (k == 39 ? (double)b2[n] : 0.0);
+          V[(size_t)k * u + n] = alpha * acc + (k == 33 ? (double)b2[n] : 0.0);
         }
       return V;
     };
@@ -1074,7 +1081,7 @@ int realnvp_tc_prepare(Flow* f) {
     const size_t qbytes = scaled ? tc::Q64_BYTES : tc::Q32_BYTES;
     for (int q = 0; q < 4; ++q) {
       uint8_t* qb = scaled ? base + (size_t)(2 + (q >> 1)) * tc::SLOT_BYTES + (q & 1) * qbytes
-                           : (q < 2 ? gb + 2 * tc::GB_CORR_BYTES + q * qbytes
+                           : (q < 2 ? gb + tc::GB_CORR_BYTES + q * qbytes
                                     : base + (size_t)2 * tc::SLOT_BYTES + (q & 1) * qbytes);
       uint16_t* c16 = reinterpret_cast<uint16_t*>(qb);
       for (int kk = 0; kk < 32; ++kk)
@@ -1088,7 +1095,7 @@ int realnvp_tc_prepare(Flow* f) {
         }
     }
     if (scaled) {
-      uint8_t* vt = gb + 2 * tc::GB_CORR_BYTES;
+      uint8_t* vt = gb + tc::GB_CORR_BYTES;
       Gemm1Writer wr{reinterpret_cast<uint16_t*>(vt), reinterpret_cast<uint16_t*>(vt + u * 64 * 2), u};
       wr.put(Vt, u, 0, tc::SO);
       overflow |= wr.overflow;
