@@ -196,7 +196,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
       "WAIT_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
-      "nanosleep.u32 64;\n\t"
+      "nanosleep.u32 500;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}\n" ::"r"(bar), "r"(parity)
