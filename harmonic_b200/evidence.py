@@ -498,3 +498,50 @@ def compute_ln_bayes_factor(ev1, ev2):
     factor = i1**2 * v2 + i2**2 * v1
     ln_bf12_std = 0.5 * np.log(factor) - 2.0 * np.log(i1)
     return (ln_bf12, ln_bf12_std)
+
+
+# ---------------------------------------------------------------------- multi-model batch (additive)
+def add_chains_batch(pairs):
+    """Fold several (Evidence, Chains) pairs -- e.g. the two models of a Bayes factor
+    (harmonic/evidence.py:534-664 takes two Evidence objects whose chains were added one after the other) -- at the
+    same time: every pair gets its own CUDA stream and host thread, so the flow + fold kernels, merges and
+    finalises of the models overlap on the GPU wherever one model's launches do not fill it (small-ndim flows,
+    short chains), and the host waits once for all of them instead of once per model.  Results are those of the
+    separate ``ev.add_chains(chains)`` calls, bit for bit.
+
+    ``pairs``: iterable of ``(evidence, chains)`` or ``(evidence, chains, kwargs_for_add_chains)``.
+    """
+    import concurrent.futures
+
+    import torch
+
+    jobs = []
+    for p in pairs:
+        ev, ch = p[0], p[1]
+        kw = p[2] if len(p) > 2 else {}
+        jobs.append((ev, ch, kw))
+    if len({id(j[0]) for j in jobs}) != len(jobs):
+        raise ValueError("every Evidence object may appear once per batch")
+    if not jobs:
+        return
+
+    def work(ev, ch, kw):
+        dev = ev.device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)  # device-resident chains may still be in flight on the caller's stream
+            with torch.cuda.stream(side):
+                ev.add_chains(ch, **kw)
+            side.synchronize()
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+        futs = [pool.submit(work, *j) for j in jobs]
+        for f in futs:
+            f.result()  # re-raises the reference's ValueErrors etc. from the worker
+
+
+def compute_ln_bayes_factor_batch(ev1, chains1, ev2, chains2):
+    """``add_chains`` of both models at once (add_chains_batch), then harmonic's ``compute_ln_bayes_factor``."""
+    add_chains_batch([(ev1, chains1), (ev2, chains2)])
+    return compute_ln_bayes_factor(ev1, ev2)

@@ -27,7 +27,13 @@ def run_capture(outdir, monkeypatch):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     monkeypatch.setattr(sys, "argv", ["capture_reference_golden.py", str(outdir)])
-    mod.main()
+    try:
+        mod.main()
+    finally:
+        # the stand-ins must not outlive the call: scipy's array-API helpers probe sys.modules["jax"]
+        for name, m in list(sys.modules.items()):
+            if (getattr(m, "__file__", None) or "").startswith(STUB):
+                del sys.modules[name]
     files = sorted(str(p) for p in outdir.glob("reference_*.npz"))
     assert len(files) == 5
     return files

@@ -216,3 +216,38 @@ def test_split_data_device_resident_chains():
     ev_d.add_chains(dte)
     assert ev_d.ln_evidence_inv == pytest.approx(ev_h.ln_evidence_inv, abs=1e-5)
     np.testing.assert_allclose(ev_d.nsamples_per_chain, ev_h.nsamples_per_chain)
+
+
+def test_add_chains_batch_equals_separate_calls():
+    """Two models of a Bayes factor (different flows, different chains) folded at the same time on two streams /
+    host threads (evidence.add_chains_batch) give, bit for bit, what the reference's order --
+    one add_chains after the other (harmonic/evidence.py:534-664 then compares the two objects) -- gives; a third
+    pair on the tensor path rides along."""
+    m1 = util.make_realnvp(5, seed=31, standardize=True, ws=0.4, temperature=0.8)
+    m2 = util.make_rqspline(5, 3, 8, (32, 32), seed=32, standardize=True, ws=0.4, temperature=0.9)
+    m3 = util.make_realnvp(64, seed=33, standardize=True, ws=0.3)
+    c1 = util.gaussian_chains(5, 40, 3000, seed=41, ragged=True)
+    c2 = util.gaussian_chains(5, 25, 4000, seed=42, ragged=True)
+    c3 = util.gaussian_chains(64, 16, 900, seed=43, ragged=True)
+    seq = [hm.Evidence(c.nchains, m) for m, c in ((m1, c1), (m2, c2), (m3, c3))]
+    for ev, c in zip(seq, (c1, c2, c3)):
+        ev.add_chains(c)
+    bat = [hm.Evidence(c.nchains, m) for m, c in ((m1, c1), (m2, c2), (m3, c3))]
+    hm.evidence.add_chains_batch(list(zip(bat, (c1, c2, c3))))
+    for a, b in zip(seq, bat):
+        assert a.ln_evidence_inv == b.ln_evidence_inv
+        assert a.ln_evidence_inv_var == b.ln_evidence_inv_var
+        assert a.ln_evidence_inv_var_var == b.ln_evidence_inv_var_var
+        np.testing.assert_array_equal(a.ln_evidence_inv_per_chain, b.ln_evidence_inv_per_chain)
+        np.testing.assert_array_equal(a.nsamples_eff_per_chain, b.nsamples_eff_per_chain)
+    # a second streaming call, and the Bayes factor of the first two
+    more1 = util.gaussian_chains(5, 40, 1000, seed=44)
+    more2 = util.gaussian_chains(5, 25, 1000, seed=45)
+    seq[0].add_chains(more1)
+    seq[1].add_chains(more2)
+    got = hm.evidence.compute_ln_bayes_factor_batch(bat[0], more1, bat[1], more2)
+    assert got == hm.evidence.compute_ln_bayes_factor(seq[0], seq[1])
+    with pytest.raises(ValueError):
+        hm.evidence.add_chains_batch([(bat[0], more1), (bat[0], more1)])
+    with pytest.raises(ValueError):  # the reference's own check, raised through the worker thread
+        hm.evidence.add_chains_batch([(bat[0], c2)])
