@@ -415,6 +415,13 @@ int hb_flow_create(const hb_flow_desc* ds, const float* weights, size_t n_weight
       const bool scaled = l < ds->n_scaled;
       off += (size_t)f->d * 128 + 128 + (scaled ? 2 : 1) * ((size_t)128 * f->u + f->u);
     }
+    // the generic kernel keeps (ndim + 128 + 2u) activation columns of 128 threads in shared memory: say at
+    // creation, not at the first predict, that a flow is too wide for it (ndim <= 163)
+    if (((size_t)D + 128 + 2 * (size_t)f->u) * 128 * sizeof(float) > 227 * 1024) {
+      hb_flow_destroy(reinterpret_cast<hb_flow*>(f));
+      set_error("RealNVP: ndim too large for the shared-memory activation layout (supported: ndim <= 163)");
+      return HB_ERR_UNSUPPORTED;
+    }
     rc = realnvp_tc_prepare(f);  // sets tc_ok when the shape is supported
   } else {
     rc = rqspline_prepare(f);

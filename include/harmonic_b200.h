@@ -112,7 +112,8 @@ int hb_device_count(void);
 size_t hb_flow_weight_count(const hb_flow_desc* desc);
 
 /* Replaces: reading model.state.params / pre_offset / pre_amp inside FlowModel.predict
- * (harmonic/model.py:222-235).  Copies and re-packs the weights on `device`. */
+ * (harmonic/model.py:222-235).  Copies and re-packs the weights on `device`.  RealNVP: 2 <= ndim <= 163 (the generic
+ * kernel keeps ndim + 128 + 2u activation columns in shared memory; wider flows return HB_ERR_UNSUPPORTED here). */
 int hb_flow_create(const hb_flow_desc* desc, const float* weights, size_t n_weights, int device,
                    hb_flow** out);
 int hb_flow_destroy(hb_flow* flow);

@@ -218,3 +218,10 @@ def test_split_data_views_and_guards():
     a, b = hm.utils.split_data(rg, 0.5)
     assert a.start_indices == [0, 3, 10] and b.start_indices == [0, 5, 7]
     np.testing.assert_array_equal(b.samples, rg.samples[10:])
+
+
+def test_realnvp_ndim_limit_is_documented_in_the_header():
+    """The generic RealNVP kernel keeps its activations in shared memory: flows wider than ndim 163 are rejected when
+    the handle is created (HB_ERR_UNSUPPORTED -> NotImplementedError), which the header says."""
+    hdr = open(os.path.join(ROOT, "include", "harmonic_b200.h")).read()
+    assert "ndim <= 163" in hdr
