@@ -162,7 +162,7 @@ def test_realnvp_tcgen05_predict(standardize, n):
     util.assert_lnphi_close(got, m2.predict(x).astype(np.float64), rel=2e-6)
 
 
-@pytest.mark.parametrize("layers", [(1, 0), (2, 4), (3, 1)])
+@pytest.mark.parametrize("layers", [(1, 0), (2, 4), (3, 1), (4, 4), (8, 0), (1, 7)])
 def test_realnvp_tcgen05_layers_nan(layers):
     m = util.make_realnvp(64, layers[0], layers[1], seed=8, ws=0.5, temperature=0.6)
     m.kernel_path = _lib.HB_PATH_TCGEN05
