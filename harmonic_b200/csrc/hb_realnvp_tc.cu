@@ -8,16 +8,18 @@
 //   3 epilogue warpgroups : each owns one tile at a time, one sample per thread (TMEM lane = sample).  A thread keeps
 //                     the 32 initially transformed features + the 7 that can enter, owned by ORIGINAL index
 //   producer warp   : streams the pre-split weight image (FP16 blocks, UMMA canonical no-swizzle K-major layout,
-//                     built once on the host) from L2 into an 8-slot ring of 20 KiB slots (3 - 4 chunks per layer) with cp.async.bulk + mbarrier
+//                     built once on the host) from L2 into an 8-slot ring of 20 KiB slots (3 - 4 chunks per layer)
+//                     with cp.async.bulk + mbarrier
 //   3 MMA warps     : tcgen05.mma issuers, warp W_MMA + t serves tile t (the first also allocates TMEM); warp-uniform
 //                     straight-line program with blocking mbarrier waits, one elected lane issues.  One issuing warp
 //                     sustains one tcgen05.mma per ~49 cycles whatever N <= 64 is, while the tensor pipe itself needs
 //                     N / 2 cycles (profiles/r2_issue_probe.txt)
+// The epilogue warpgroups run with 160 registers, the producer / MMA warpgroup with 32 (setmaxnreg).
 //
 // Arithmetic.  leaky_relu(h) = a h + b |h| with a = (1 + 0.01) / 2, b = (1 - 0.01) / 2 (harmonic/flows.py:170
 // LeakyReLU slope 0.01), so with H = x' W0' (x' = conditioning inputs + constant one, W0' = [W0 ; b0]) a coupling MLP is
 //     O = leaky_relu(H) W2 + b2 = x' V + |H| U,     V = a W0' W2 (+ b2 on the constant row),  U = b W2
-// V (40 x 32) is formed once on the host in float64.  The linear term rides in GEMM1 as 32 more output columns
+// V (34 x 32) is formed once on the host in float64.  The linear term rides in GEMM1 as 32 more output columns
 // (N = 160: [W0' | V]); the epilogue between the GEMMs (E1) is then only |H| and its FP16 split -- no activation,
 // no bias, nothing but conversions -- which is what the kernel's issue slots go to (profiles/r2_alu_probe.txt).
 //
@@ -27,7 +29,7 @@
 //   GEMM2  O[128 x 32] += |H|[:, quarter] . U[quarter, :]                    A from TMEM, 6 FP16 MMAs per K = 32 quarter
 //   E2     y -= O (shift) or softplus-clip scale epilogue on y, log-det
 // Scaled layers run GEMM1 with V_scale, GEMM2 with U_scale, hand O to the epilogue, then a second pass O = x' V_shift
-// (8 small MMAs) + |H| U_shift over the same operands, which runs under the softplus / reciprocal / log-det arithmetic.
+// (7 small MMAs) + |H| U_shift over the same operands, which runs under the softplus / reciprocal / log-det arithmetic.
 //
 // Split-precision contractions with FP32 accumulation in TMEM, float32-equivalent products (~2^-22), every MMA
 // kind::f16.  A weight is w_hi (11 significant bits) + w_lo; an activation a is hs = fp16(a) (round to nearest) and
