@@ -16,20 +16,21 @@
 //                     N / 2 cycles (profiles/r2_issue_probe.txt)
 // The epilogue warpgroups run with 160 registers, the producer / MMA warpgroup with 32 (setmaxnreg).
 //
-// Arithmetic.  leaky_relu(h) = a h + b |h| with a = (1 + 0.01) / 2, b = (1 - 0.01) / 2 (harmonic/flows.py:170
+// Arithmetic.  leaky_relu(h) = a h + b relu(h) with a = 0.01, b = 1 - 0.01 (harmonic/flows.py:170
 // LeakyReLU slope 0.01), so with H = x' W0' (x' = conditioning inputs + constant one, W0' = [W0 ; b0]) a coupling MLP is
-//     O = leaky_relu(H) W2 + b2 = x' V + |H| U,     V = a W0' W2 (+ b2 on the constant row),  U = b W2
+//     O = leaky_relu(H) W2 + b2 = x' V + relu(H) U,  V = a W0' W2 (+ b2 on the constant row),  U = b W2
 // V (34 x 32) is formed once on the host in float64.  The linear term rides in GEMM1 as 32 more output columns
-// (N = 160: [W0' | V]); the epilogue between the GEMMs (E1) is then only |H| and its FP16 split -- no activation,
+// (N = 160: [W0' | V]); the epilogue between the GEMMs (E1) is then only relu(H) and its FP16 split -- and the clamp
+// is a modifier of the conversion instructions: no arithmetic for the activation,
 // no bias, nothing but conversions -- which is what the kernel's issue slots go to (profiles/r2_alu_probe.txt).
 //
 // Per coupling layer and tile
 //   GEMM1  [H | O] [128 x 160] = [32 input slots | newest column | 1] . [W0' | V]   A, B from shared memory, 7 MMAs
-//   E1     |H| -> FP16 pair (hs, |H| - hs), in place of H                    eight 16-column chunks, loads prefetched
-//   GEMM2  O[128 x 32] += |H|[:, quarter] . U[quarter, :]                    A from TMEM, 6 FP16 MMAs per K = 32 quarter
+//   E1     r = relu(H) -> FP16 pair (hs, r - hs), in place of H              eight 16-column chunks, loads prefetched
+//   GEMM2  O[128 x 32] += r[:, quarter] . U[quarter, :]                      A from TMEM, 6 FP16 MMAs per K = 32 quarter
 //   E2     y -= O (shift) or softplus-clip scale epilogue on y, log-det
 // Scaled layers run GEMM1 with V_scale, GEMM2 with U_scale, hand O to the epilogue, then a second pass O = x' V_shift
-// (7 small MMAs) + |H| U_shift over the same operands, which runs under the softplus / reciprocal / log-det arithmetic.
+// (7 small MMAs) + relu(H) U_shift over the same operands, which runs under the softplus / reciprocal / log-det arithmetic.
 //
 // Split-precision contractions with FP32 accumulation in TMEM, float32-equivalent products (~2^-22), every MMA
 // kind::f16.  A weight is w_hi (11 significant bits) + w_lo; an activation a is hs = fp16(a) (round to nearest) and
@@ -37,12 +38,12 @@
 //     a w ~= hs w_hi + lo w_hi + hs w_lo                                       (the lo w_lo term, <= 2^-22, dropped)
 // with s = 1 everywhere: hs = fp16(a) straight out of the register / accumulator and lo = a - hs by ONE
 // mixed-precision FMA (FHFMA), both against the SAME hi block.  So that w_lo stays a normal half the weights travel
-// scaled: H accumulates SH = 2^5 times its value (|H| is positively homogeneous, E1 does not care), O accumulates
+// scaled: H accumulates SH = 2^5 times its value (relu is positively homogeneous, E1 does not care), O accumulates
 // SO = 2^10 times its value; E2 removes the factor inside its FMA.
 // What remains against a float32 FMA chain is the tensor cores' truncating accumulator
 // (profiles/r1_tensor_accum_rounding.txt), see DESIGN.md 4.1.
 //
-// Range guard.  hs = fp16(|H|) needs |H| < 65504 and the truncating accumulator costs accuracy where the flow is
+// Range guard.  hs = fp16(relu(H)) needs H < 65504 and the truncating accumulator costs accuracy where the flow is
 // evaluated far outside its trained range.  Every epilogue thread tracks max |conditioning input| of its rows (the 32
 // raw features and each layer's new column); rows beyond Params::guard_limit are counted into a device counter which
 // the host reads with the results and answers by re-evaluating the call on the CUDA-core path (hb_api / evidence.py).
@@ -250,6 +251,18 @@ __device__ __forceinline__ uint32_t pack_f16x2(float hi_elem, float lo_elem) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
   return d;
 }
+// the same with negative inputs clamped to zero (NaN stays NaN); RZ: round towards zero, so that the remainder of a
+// positive value is never negative
+__device__ __forceinline__ uint32_t pack_relu_rz_f16x2(float hi_elem, float lo_elem) {
+  uint32_t d;
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float hi_elem, float lo_elem) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
 __device__ __forceinline__ uint16_t to_f16(float v) {
   uint16_t d;
   asm("cvt.rn.f16.f32 %0, %1;" : "=h"(d) : "f"(v));
@@ -414,17 +427,19 @@ __device__ __forceinline__ void split_x_pair(float va, float vb, uint32_t& hs, u
   lo = pack_f16x2(lb, la);
 }
 
-// E1 for one 16-column chunk of H: wh = 8 words of packed hs = fp16(|H|) pairs, wl = 8 words of packed fp16(|H| - hs)
-// pairs.  Per pair: F2FP, LOP3, 2 FHFMA, F2FP.
+// E1 for one 16-column chunk of H: r = relu(H) as wh = 8 words of packed hs = fp16(r) pairs (rounded towards zero) and
+// wl = 8 words of packed fp16(r - hs) pairs.  Per pair: F2FP.RELU.RZ, 2 FHFMA, F2FP.RELU -- the clamp is part of the
+// conversions: for H < 0, hs = 0 and the "remainder" H - 0 < 0 is clamped by the second one; for H > 0 the remainder
+// is non-negative because hs was rounded towards zero.
 __device__ __forceinline__ void e1_chunk(const uint32_t (&v)[16], uint32_t (&wl)[8], uint32_t (&wh)[8]) {
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
     const float h0 = __uint_as_float(v[2 * jj]), h1 = __uint_as_float(v[2 * jj + 1]);
-    const uint32_t hs = pack_f16x2(h1, h0) & 0x7fff7fffu;
+    const uint32_t hs = pack_relu_rz_f16x2(h1, h0);
     float l0, l1;
-    split_rest<true>(hs, h0, h1, l0, l1);
+    split_rest<false>(hs, h0, h1, l0, l1);
     wh[jj] = hs;
-    wl[jj] = pack_f16x2(l1, l0);
+    wl[jj] = pack_relu_f16x2(l1, l0);
   }
 }
 
@@ -616,7 +631,7 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
           TR(26 + q);
         }
         if (scaled) {
-          // ---- second pass: O = x' V_shift + |H| U_shift (rows 0..31 of each quarter block) once the epilogue has
+          // ---- second pass: O = x' V_shift + relu(H) U_shift (rows 0..31 of each quarter block) once the epilogue has
           // read the scale pre-activations out of O
           mbar_wait(BAR(B_OCONS + t), pit & 1);
           ++pit;
@@ -1027,7 +1042,7 @@ int realnvp_tc_prepare(Flow* f) {
   if (nl > tc::MAX_TC_LAYERS) return HB_OK;
   const int d = f->d, u = f->u;
   if (d != tc::DH || u != tc::U) return HB_OK;
-  const double alpha = 0.5 * (1.0 + tc::LEAKY_SLOPE), beta = 0.5 * (1.0 - tc::LEAKY_SLOPE);
+  const double alpha = tc::LEAKY_SLOPE, beta = 1.0 - tc::LEAKY_SLOPE;  // leaky_relu(h) = alpha h + beta relu(h)
   size_t nchunks = 0;
   for (int l = 0; l < nl; ++l) nchunks += tc::layer_chunks(l < ds.n_scaled);
   std::vector<uint8_t> img(nchunks * tc::SLOT_BYTES, 0);

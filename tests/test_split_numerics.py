@@ -4,10 +4,13 @@ harmonic_b200/csrc/hb_realnvp_tc.cu): numpy float16 stands in for the tensor cor
   activation a -> hs = fp16(a) (round to nearest), lo = fp16(a - hs)          (the difference is exact in float32)
   weight     w -> w_hi = top 11 significant bits, w_lo = w - w_hi, stored as fp16(w_hi * S), fp16(w_lo * S)
   S * a * w ~= hs * (w_hi S) + lo * (w_hi S) + hs * (w_lo S)                   (lo * w_lo, <= 2^-22 relative, dropped)
-  leaky_relu(h) = a h + b |h|  =>  leaky_relu(x' W0') W2 + b2 = x' V + |x' W0'| U,  V = a W0' W2 (+ b2), U = b W2
+  leaky_relu(h) = a h + b relu(h) (a = 0.01, b = 0.99)  =>  leaky_relu(x' W0') W2 + b2 = x' V + relu(x' W0') U,
+      V = a W0' W2 (+ b2), U = b W2
+  hidden activation r = relu(h) -> hs = fp16(r) rounded TOWARDS ZERO, lo = fp16(max(h - hs, 0))   (the clamp is a modifier
+      of both conversion instructions: h < 0 gives hs = 0 and a negative "remainder" h that the second one clamps)
 
 The tests pin the claims the design rests on: float32-equivalent products over the guarded range, graceful behaviour
-in the half subnormal range, what a cheaper split would cost, and that the linear / absolute-value decomposition of a
+in the half subnormal range, what a cheaper split would cost, and that the linear / relu decomposition of a
 coupling MLP evaluated with these products stays at the float32 level against the float64 MLP."""
 import numpy as np
 
@@ -30,6 +33,19 @@ def split_weight(w, scale=S):
     big = np.abs(hi * scale) >= np.float32(2.0 ** -14)
     assert np.array_equal(b_hi.astype(np.float32)[big], (hi * scale)[big])  # an 11-bit significand is exactly a (normal) half
     return b_hi.astype(np.float64), b_lo.astype(np.float64)
+
+
+def split_relu_rz(h):
+    """E1 of the kernel: cvt.rz.relu.f16x2.f32, h - hs by one mixed-precision FMA (exact), cvt.rn.relu.f16x2.f32."""
+    h = h.astype(np.float32)
+    r = np.maximum(h, np.float32(0))
+    hs = r.astype(np.float16)
+    over = hs.astype(np.float32) > r
+    hs = np.where(over, np.nextafter(hs, np.float16(0)), hs).astype(np.float16)
+    rest = h - hs.astype(np.float32)
+    assert (rest[h > 0] >= 0).all()  # rounded towards zero: the remainder of a positive value is never negative
+    lo = np.maximum(rest, np.float32(0)).astype(np.float16)
+    return hs.astype(np.float64), lo.astype(np.float64)
 
 
 def three_products(a, w):
@@ -93,16 +109,16 @@ def test_cheaper_splits_are_not_float32_equivalent():
         assert rel.max() > 2.0 ** -13
 
 
-def split_matmul(a, w, scale):
+def split_matmul(a, w, scale, split=split_activation):
     """(a @ w) * scale with the three-product scheme, float64 accumulation of the exact FP16 products."""
-    hs, lo = split_activation(a)
+    hs, lo = split(a)
     b_hi, b_lo = split_weight(w, np.float32(scale))
     return hs @ b_hi + lo @ b_hi + hs @ b_lo
 
 
-def test_coupling_mlp_as_linear_plus_absolute_value_term():
+def test_coupling_mlp_as_linear_plus_relu_term():
     """O = leaky_relu(x W0 + b0) W2 + b2 evaluated as the kernel does -- H' = 32 [x | 1] W0', O' = 1024 ([x | 1] V +
-    |H| U) with V = a W0' W2 (+ b2 on the constant row) formed in float64 and rounded to float32, every contraction by
+    relu(H) U) with V = a W0' W2 (+ b2 on the constant row) formed in float64 and rounded to float32, every contraction by
     the three-product FP16 scheme -- against the float64 MLP: the error stays at the level of a float32 evaluation."""
     rng = np.random.default_rng(3)
     n, d, hidden, u = 4000, 32, 128, 32
@@ -111,7 +127,7 @@ def test_coupling_mlp_as_linear_plus_absolute_value_term():
     b0 = (rng.standard_normal(hidden) * 0.1).astype(np.float32)
     W2 = (rng.standard_normal((hidden, u)) * 0.15 / np.sqrt(hidden) * 8).astype(np.float32)
     b2 = (rng.standard_normal(u) * 0.1).astype(np.float32)
-    a_lin, b_abs = 0.5 * (1 + 0.01), 0.5 * (1 - 0.01)
+    a_lin, b_abs = 0.01, 1 - 0.01
     x1 = np.concatenate([x, np.ones((n, 1), np.float32)], axis=1)
     W0p = np.concatenate([W0, b0[None, :]], axis=0).astype(np.float64)
     V = a_lin * W0p @ W2.astype(np.float64)
@@ -120,7 +136,7 @@ def test_coupling_mlp_as_linear_plus_absolute_value_term():
     # kernel arithmetic
     H32 = split_matmul(x1, W0p.astype(np.float32), 32.0).astype(np.float32)  # what E1 reads from the accumulator
     Olin = split_matmul(x1, V.astype(np.float32), 1024.0)
-    Oabs = split_matmul(np.abs(H32), U, 32.0)
+    Oabs = split_matmul(H32, U, 32.0, split_relu_rz)
     got = (Olin + Oabs) / 1024.0
     # float64 truth and a float32 evaluation of the reference formula
     H = x1.astype(np.float64) @ W0p
@@ -131,3 +147,18 @@ def test_coupling_mlp_as_linear_plus_absolute_value_term():
     scale = np.abs(np.where(H > 0, H, 0.01 * H)) @ np.abs(W2.astype(np.float64)) + np.abs(b2)  # conditioning of the sum
     assert (err / scale).max() < 2.0 ** -20
     assert np.sqrt(np.mean(err ** 2)) < 3.0 * np.sqrt(np.mean(err32 ** 2)) + 1e-7
+
+
+def test_relu_split_rounded_towards_zero_keeps_21_bits():
+    """hs rounded towards zero leaves a remainder below one half-precision ulp of r (11 significant bits after the
+    second conversion): r = hs + lo to 2^-21 relative in the normal range, exactly zero for h <= 0, NaN stays NaN."""
+    rng = np.random.default_rng(5)
+    h = (rng.standard_normal(200000) * np.exp(rng.uniform(np.log(0.25), np.log(6.0e4), 200000))).astype(np.float32)
+    h = h[np.abs(h) < 65000]
+    hs, lo = split_relu_rz(h)
+    r = np.maximum(h.astype(np.float64), 0)
+    assert (hs[h <= 0] == 0).all() and (lo[h <= 0] == 0).all()
+    pos = h > 0.25
+    assert (np.abs(hs + lo - r)[pos] <= 2.0 ** -21 * r[pos]).all()
+    hs, lo = split_relu_rz(np.array([np.nan, -np.inf], np.float32))
+    assert np.isnan(hs[0]) and hs[1] == 0 and lo[1] == 0
