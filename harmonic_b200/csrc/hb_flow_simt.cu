@@ -143,35 +143,109 @@ realnvp_simt_kernel(RealNVPSimtParams P, const XT* __restrict__ x, long long ld,
 }
 
 // ------------------------------------------------------------------------------------------
-// RealNVP, small ndim (2..8): everything in registers, two samples per thread, all layers'
-// weights resident in shared memory as per-hidden-unit records
-//   rec[j] = { b0[j], W0[0..d-1][j], Wt[j][0..u-1], Ws[j][0..u-1] }   (padded to 4 floats)
-// so one warp-uniform LDS.128 stream feeds (d + 2u + 2) FMAs per sample and hidden unit; the
-// hidden activation is never stored.
+// RealNVP, small ndim (2..8): everything in registers, SM_R samples per thread (4 up to ndim 5, else 2),
+// all layers' weights resident in shared memory as per-hidden-unit records
+//   scaled layer    rec[j] = { b0[j], W0[0..d-1][j], c Wt[j][0..u-1], c Ws[j][0..u-1] }   (padded to 4 floats)
+//   unscaled layer  rec[j] = { b0[j], W0[0..d-1][j], c Wt[j][0..u-1] }
+// so one warp-uniform LDS.128 stream feeds d + 1 + 2u (resp. d + 1 + u) arithmetic instructions per sample and
+// hidden unit; the hidden activation is never stored.  leaky_relu(h) = s h + c relu(h) with s = 0.01, c = 1 - s
+// (harmonic/flows.py:170): the linear part of a coupling MLP, s (y W0 + b0) W2 + b2 = y V + v0, is a d x 2u matrix
+// formed once on the host in float64 (the tail of each layer's block) and seeds the output accumulators, the loop over
+// the hidden units keeps only relu -- one FMNMX instead of FMUL + FMNMX per sample and hidden unit.
 // ------------------------------------------------------------------------------------------
 constexpr int SM_THREADS = 256;  // (128 -> 256: 32 instead of 16 resident warps per SM at cfg3, 5.04 -> 4.61 ms)
-constexpr int SM_R = 2;  // samples per thread
+constexpr int small_r(int D) { return D <= 5 ? 4 : 2; }  // samples per thread
+constexpr int small_d(int D) { return (D == 2) ? 1 : (D == 3) ? 2 : (D == 4) ? 2 : (D == 5) ? 2 : (D == 6) ? 3 : 4; }
 
 struct SmallParams {
-  const float* pack;   // per layer: 128 records of `rp` floats, then bt[4-padded u], bs[4-padded u]
+  const float* pack;   // scaled layers first: 128 records + tail each; tail = (1 + d) rows of 2 x (4-padded u) floats
   const float* pre;    // pre_offset[D], pre_amp[D] or nullptr
-  int nlayers, nscaled, rp, layer_floats;
+  int nlayers, nscaled, total_floats;
+  int lf_scaled, lf_unscaled;  // floats per layer block
   float T, sum_log_amp;
   int x_f64, lp_f64;
 };
+
+// One coupling layer for the R samples of a thread.  L: the layer's block in shared memory.
+template <int D, int R, bool SCALED>
+__device__ __forceinline__ void small_layer(const float* __restrict__ L, float (&y)[R][D], float (&ldj)[R]) {
+  constexpr int d = small_d(D), u = D - d, UP = (u + 3) & ~3;
+  constexpr int NW = 1 + d + (SCALED ? 2 * u : u);
+  constexpr int RP = (NW + 3) & ~3;
+  const float* tail = L + 128 * RP;
+  float sh[R][u], sc[R][SCALED ? u : 1];
+#pragma unroll
+  for (int k = 0; k < u; ++k) {
+    float vt[1 + d], vs[1 + d];
+#pragma unroll
+    for (int i = 0; i <= d; ++i) {
+      vt[i] = tail[i * 2 * UP + k];
+      vs[i] = SCALED ? tail[i * 2 * UP + UP + k] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      float t = vt[0], s = vs[0];
+#pragma unroll
+      for (int i = 0; i < d; ++i) {
+        t = fmaf(y[q][i], vt[1 + i], t);
+        if (SCALED) s = fmaf(y[q][i], vs[1 + i], s);
+      }
+      sh[q][k] = t;
+      if (SCALED) sc[q][k] = s;
+    }
+  }
+#pragma unroll 4
+  for (int j = 0; j < 128; ++j) {
+    const float* rec = L + j * RP;
+    float w[RP];
+#pragma unroll
+    for (int i = 0; i < RP; i += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(rec + i);
+      w[i] = t4.x;
+      w[i + 1] = t4.y;
+      w[i + 2] = t4.z;
+      w[i + 3] = t4.w;
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      float h = w[0];
+#pragma unroll
+      for (int i = 0; i < d; ++i) h = fmaf(y[q][i], w[1 + i], h);
+      h = fmaxf(h, 0.f);
+#pragma unroll
+      for (int k = 0; k < u; ++k) {
+        sh[q][k] = fmaf(h, w[1 + d + k], sh[q][k]);
+        if (SCALED) sc[q][k] = fmaf(h, w[1 + d + u + k], sc[q][k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+#pragma unroll
+    for (int k = 0; k < u; ++k) {
+      float y1 = y[q][d + k] - sh[q][k];
+      if (SCALED) {
+        float s = softplus_acc(sc[q][k]);
+        s = fminf(fmaxf(s, 1e-3f), 1e3f);
+        s = (sc[q][k] != sc[q][k]) ? sc[q][k] : s;
+        y1 = y1 / s;
+        ldj[q] -= logf(s);
+      }
+      y[q][d + k] = y1;
+    }
+  }
+}
 
 template <int D, bool FOLD>
 __global__ void __launch_bounds__(SM_THREADS)
 realnvp_small_kernel(SmallParams P, const void* __restrict__ xv, long long ld,
                      const void* __restrict__ lnpostv, float* __restrict__ lnpred_out, FoldParams fp,
                      long long nrows, long long rows_per_cta) {
-  constexpr int d = (D == 2) ? 1 : (D == 3) ? 2 : (D == 4) ? 2 : (D == 5) ? 2 : (D == 6) ? 3 : (D == 7) ? 4 : 4;
-  constexpr int u = D - d;
-  constexpr int UP = (u + 3) & ~3;
+  constexpr int SM_R = small_r(D);
   extern __shared__ float wsm[];
   __shared__ double scratch[3 * (SM_THREADS / 32)];
   const int tid = threadIdx.x;
-  for (int i = tid; i < P.nlayers * P.layer_floats; i += SM_THREADS) wsm[i] = P.pack[i];
+  for (int i = tid; i < P.total_floats; i += SM_THREADS) wsm[i] = P.pack[i];
   __syncthreads();
   const long long row_lo = (long long)blockIdx.x * rows_per_cta;
   long long row_hi = row_lo + rows_per_cta;
@@ -180,7 +254,6 @@ realnvp_small_kernel(SmallParams P, const void* __restrict__ xv, long long ld,
   Fold<SM_THREADS> fold(fp, blockIdx.x, tid, scratch, (FOLD && had_rows) ? row_lo : 0);
   const float invT = 1.f / P.T;
   const float base_const = -(float)D * logf(P.T) - 0.5f * (float)D * 1.8378770664093453f;
-  const int rp = P.rp;
 
   for (long long t0 = row_lo; t0 < row_hi; t0 += SM_THREADS * SM_R) {
     float y[SM_R][D];
@@ -200,57 +273,18 @@ realnvp_small_kernel(SmallParams P, const void* __restrict__ xv, long long ld,
       }
       ldj[q] = 0.f;
     }
+    // relu swallows a NaN hidden unit (fmaxf(NaN, 0) = 0) where leaky_relu propagates it; the linear term y V + v0
+    // keeps the propagation: it multiplies EVERY conditioning input (NaN * 0 = NaN, inf * v = +-inf or NaN), so a
+    // non-finite input still ends in a non-finite ln phi (tests/test_gpu_flows.py::test_nan_propagates).
     for (int l = 0; l < P.nlayers; ++l) {
-      const float* L = wsm + (size_t)l * P.layer_floats;
-      const bool scaled = l < P.nscaled;
-      float sh[SM_R][u], sc[SM_R][u];
-#pragma unroll
-      for (int q = 0; q < SM_R; ++q)
-#pragma unroll
-        for (int k = 0; k < u; ++k) {
-          sh[q][k] = L[128 * rp + k];
-          sc[q][k] = L[128 * rp + UP + k];
-        }
-#pragma unroll 4
-      for (int j = 0; j < 128; ++j) {
-        const float* rec = L + j * rp;
-        float w[1 + d + 2 * u];
-#pragma unroll
-        for (int i = 0; i < 1 + d + 2 * u; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(rec + i);
-          w[i] = t4.x;
-          if (i + 1 < 1 + d + 2 * u) w[i + 1] = t4.y;
-          if (i + 2 < 1 + d + 2 * u) w[i + 2] = t4.z;
-          if (i + 3 < 1 + d + 2 * u) w[i + 3] = t4.w;
-        }
+      if (l < P.nscaled)
+        small_layer<D, SM_R, true>(wsm + (size_t)l * P.lf_scaled, y, ldj);
+      else
+        small_layer<D, SM_R, false>(wsm + (size_t)P.nscaled * P.lf_scaled + (size_t)(l - P.nscaled) * P.lf_unscaled,
+                                    y, ldj);
+      if (l + 1 < P.nlayers) {  // inverse permute: rotate left by one
 #pragma unroll
         for (int q = 0; q < SM_R; ++q) {
-          float h = w[0];
-#pragma unroll
-          for (int i = 0; i < d; ++i) h = fmaf(y[q][i], w[1 + i], h);
-          h = fmaxf(h, 0.01f * h);
-#pragma unroll
-          for (int k = 0; k < u; ++k) {
-            sh[q][k] = fmaf(h, w[1 + d + k], sh[q][k]);
-            sc[q][k] = fmaf(h, w[1 + d + u + k], sc[q][k]);  // zero weights for unscaled layers
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < SM_R; ++q) {
-#pragma unroll
-        for (int k = 0; k < u; ++k) {
-          float y1 = y[q][d + k] - sh[q][k];
-          if (scaled) {
-            float s = softplus_acc(sc[q][k]);
-            s = fminf(fmaxf(s, 1e-3f), 1e3f);
-            s = (sc[q][k] != sc[q][k]) ? sc[q][k] : s;
-            y1 = y1 / s;
-            ldj[q] -= logf(s);
-          }
-          y[q][d + k] = y1;
-        }
-        if (l + 1 < P.nlayers) {  // inverse permute: rotate left by one
           const float y0 = y[q][0];
 #pragma unroll
           for (int i = 0; i < D - 1; ++i) y[q][i] = y[q][i + 1];
@@ -551,12 +585,15 @@ struct RQFastParams {
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
-  // |x| < 0.25: odd series (rel. err < 2e-7); else 1 - 2 / (exp(2x) + 1) with MUFU ex2 / rcp
-  const float x2 = x * x;
-  const float ser = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.13333334f), -0.33333334f), 1.0f);
-  const float e = exp2f(2.8853900817779268f * fabsf(x));  // exp(2|x|)
-  const float big = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
-  return (fabsf(x) < 0.25f) ? ser : big;
+  // tanh|x| = (1 - e) / (1 + e) with e = exp(-2|x|) in (0, 1] (MUFU ex2 / rcp): seven instructions.  The ABSOLUTE
+  // error is <= ~1.5e-7 everywhere (e carries 2^-22 relative, i.e. <= 2.4e-7 absolute, halved by the quotient's
+  // slope at 0); the relative error grows towards x = 0 (cancellation in 1 - e), which does not matter here: every
+  // tanh output only enters FMAs against the next Dense's weights and bias, where its absolute error counts like the
+  // rounding of any other O(1) float32 term (round 1 carried an odd series for |x| < 0.25 beside this: twice the
+  // instructions for no difference in ln phi at the 1e-7 level, profiles/README.md).
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * fabsf(x)));
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
 }
 
 // distrax RationalQuadraticSpline forward, K = 8, parameters in registers (static indexing only)
@@ -904,45 +941,62 @@ static int realnvp_small_prepare(Flow* f, SmallParams* P) {
     *P = static_cast<SmallCache*>(f->small_cache)->P;
     return HB_OK;
   }
-  const int d = f->d, u = f->u, nl = f->nlayers;
-  const int rp = (1 + d + 2 * u + 3) & ~3;
+  const int d = f->d, u = f->u, nl = f->nlayers, ns = f->desc.n_scaled;
   const int up = (u + 3) & ~3;
-  const int layer_floats = 128 * rp + 2 * up;
-  std::vector<float> pack((size_t)nl * layer_floats, 0.f);
+  const int rp_s = (1 + d + 2 * u + 3) & ~3, rp_u = (1 + d + u + 3) & ~3;
+  const int tail = (1 + d) * 2 * up;
+  const int lf_s = 128 * rp_s + tail, lf_u = 128 * rp_u + tail;
+  const double slope = 0.01, c = 1.0 - slope;  // leaky_relu(h) = slope h + c relu(h)
+  std::vector<float> pack((size_t)ns * lf_s + (size_t)(nl - ns) * lf_u, 0.f);
   const float* w = f->host_weights.data();
   for (int l = 0; l < nl; ++l) {
-    const bool scaled = l < f->desc.n_scaled;
+    const bool scaled = l < ns;
+    const int rp = scaled ? rp_s : rp_u;
     const float* W0 = w + f->layer_off[l];
     const float* b0 = W0 + (size_t)d * 128;
     const float* Wt = b0 + 128;
     const float* bt = Wt + (size_t)128 * u;
     const float* Ws = bt + u;
     const float* bs = Ws + (size_t)128 * u;
-    float* L = pack.data() + (size_t)l * layer_floats;
+    float* L = pack.data() + (scaled ? (size_t)l * lf_s : (size_t)ns * lf_s + (size_t)(l - ns) * lf_u);
     for (int j = 0; j < 128; ++j) {
       float* rec = L + (size_t)j * rp;
       rec[0] = b0[j];
       for (int i = 0; i < d; ++i) rec[1 + i] = W0[(size_t)i * 128 + j];
-      for (int k = 0; k < u; ++k) rec[1 + d + k] = Wt[(size_t)j * u + k];
+      for (int k = 0; k < u; ++k) rec[1 + d + k] = (float)(c * (double)Wt[(size_t)j * u + k]);
       if (scaled)
-        for (int k = 0; k < u; ++k) rec[1 + d + u + k] = Ws[(size_t)j * u + k];
+        for (int k = 0; k < u; ++k) rec[1 + d + u + k] = (float)(c * (double)Ws[(size_t)j * u + k]);
     }
-    for (int k = 0; k < u; ++k) L[128 * rp + k] = bt[k];
-    if (scaled)
-      for (int k = 0; k < u; ++k) L[128 * rp + up + k] = bs[k];
+    // linear part: row 0 = b2 + slope b0 W2, rows 1..d = slope W0 W2 (float64 sums, rounded once)
+    float* tl = L + (size_t)128 * rp;
+    for (int half = 0; half < (scaled ? 2 : 1); ++half) {
+      const float* W2 = half ? Ws : Wt;
+      const float* b2 = half ? bs : bt;
+      for (int k = 0; k < u; ++k) {
+        double v0 = (double)b2[k];
+        for (int j = 0; j < 128; ++j) v0 += slope * (double)b0[j] * (double)W2[(size_t)j * u + k];
+        tl[half * up + k] = (float)v0;
+        for (int i = 0; i < d; ++i) {
+          double v = 0.0;
+          for (int j = 0; j < 128; ++j) v += (double)W0[(size_t)i * 128 + j] * (double)W2[(size_t)j * u + k];
+          tl[(size_t)(1 + i) * 2 * up + half * up + k] = (float)(slope * v);
+        }
+      }
+    }
   }
-  SmallCache* c = new SmallCache();
-  HB_CUDA(cudaMalloc(&c->dev, pack.size() * sizeof(float)));
-  HB_CUDA(cudaMemcpy(c->dev, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
-  c->P.pack = c->dev;
-  c->P.pre = f->desc.standardize ? f->dev_weights : nullptr;
-  c->P.nlayers = nl;
-  c->P.nscaled = f->desc.n_scaled;
-  c->P.rp = rp;
-  c->P.layer_floats = layer_floats;
-  c->P.sum_log_amp = f->sum_log_amp;
-  f->small_cache = c;
-  *P = c->P;
+  SmallCache* cch = new SmallCache();
+  HB_CUDA(cudaMalloc(&cch->dev, pack.size() * sizeof(float)));
+  HB_CUDA(cudaMemcpy(cch->dev, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
+  cch->P.pack = cch->dev;
+  cch->P.pre = f->desc.standardize ? f->dev_weights : nullptr;
+  cch->P.nlayers = nl;
+  cch->P.nscaled = ns;
+  cch->P.total_floats = (int)pack.size();
+  cch->P.lf_scaled = lf_s;
+  cch->P.lf_unscaled = lf_u;
+  cch->P.sum_log_amp = f->sum_log_amp;
+  f->small_cache = cch;
+  *P = cch->P;
   return HB_OK;
 }
 
@@ -970,6 +1024,23 @@ static int small_launch(const SmallParams& P, bool fold, int grid, size_t smem, 
   return HB_OK;
 }
 
+// resident CTAs per SM of the instantiation a call will launch (registers and shared memory)
+template <int D>
+static int small_occupancy(bool fold, size_t smem) {
+  int nb = 0;
+  cudaError_t e;
+  if (fold) {
+    auto k = realnvp_small_kernel<D, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, SM_THREADS, smem);
+  } else {
+    auto k = realnvp_small_kernel<D, false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, SM_THREADS, smem);
+  }
+  return (e == cudaSuccess && nb > 0) ? nb : 1;
+}
+
 // returns HB_ERR_UNSUPPORTED (without setting an error) when the shape does not fit this path
 static int realnvp_small_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
                              const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
@@ -980,17 +1051,24 @@ static int realnvp_small_run(Flow* f, float T, const void* x, int x_dtype, long 
   SmallParams P;
   int rc = realnvp_small_prepare(f, &P);
   if (rc) return rc;
-  const size_t smem = (size_t)P.nlayers * P.layer_floats * sizeof(float);
+  const size_t smem = (size_t)P.total_floats * sizeof(float);
   if (smem > 200 * 1024) return HB_ERR_UNSUPPORTED;
   P.T = T;
   P.x_f64 = x_dtype == HB_F64;
   P.lp_f64 = lp_dtype == HB_F64;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-  int per_sm = (int)((227 * 1024) / (smem + 2048));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  const long long tile = SM_THREADS * SM_R;
+  int per_sm = 1;
+  switch (D) {
+    case 2: per_sm = small_occupancy<2>(acc != nullptr, smem); break;
+    case 3: per_sm = small_occupancy<3>(acc != nullptr, smem); break;
+    case 4: per_sm = small_occupancy<4>(acc != nullptr, smem); break;
+    case 5: per_sm = small_occupancy<5>(acc != nullptr, smem); break;
+    case 6: per_sm = small_occupancy<6>(acc != nullptr, smem); break;
+    case 7: per_sm = small_occupancy<7>(acc != nullptr, smem); break;
+    default: per_sm = small_occupancy<8>(acc != nullptr, smem); break;
+  }
+  const long long tile = SM_THREADS * small_r(D);
   long long nfl = (long long)sms * per_sm;
   long long rpc = (n + nfl - 1) / nfl;
   rpc = ((rpc + tile - 1) / tile) * tile;
