@@ -236,8 +236,11 @@ __device__ __forceinline__ void small_layer(const float* __restrict__ L, float (
   }
 }
 
+#ifndef HB_SMALL_MINB
+#define HB_SMALL_MINB 1
+#endif
 template <int D, bool FOLD>
-__global__ void __launch_bounds__(SM_THREADS)
+__global__ void __launch_bounds__(SM_THREADS, HB_SMALL_MINB)
 realnvp_small_kernel(SmallParams P, const void* __restrict__ xv, long long ld,
                      const void* __restrict__ lnpostv, float* __restrict__ lnpred_out, FoldParams fp,
                      long long nrows, long long rows_per_cta) {
