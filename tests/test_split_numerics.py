@@ -162,3 +162,26 @@ def test_relu_split_rounded_towards_zero_keeps_21_bits():
     assert (np.abs(hs + lo - r)[pos] <= 2.0 ** -21 * r[pos]).all()
     hs, lo = split_relu_rz(np.array([np.nan, -np.inf], np.float32))
     assert np.isnan(hs[0]) and hs[1] == 0 and lo[1] == 0
+
+
+def test_register_kernel_linear_plus_relu_form():
+    """realnvp_small_kernel evaluates a coupling MLP as y V + v0 + relu(y W0 + b0) (0.99 W2) with
+    V = 0.01 W0 W2 and v0 = b2 + 0.01 b0 W2 formed in float64 and rounded to float32 once: in float32 arithmetic the
+    form is as close to the float64 MLP as the float32 evaluation of leaky_relu(y W0 + b0) W2 + b2 itself."""
+    rng = np.random.default_rng(11)
+    n, d, hidden, u = 5000, 2, 128, 3
+    y = (rng.standard_normal((n, d)) * 1.5).astype(np.float32)
+    W0 = (rng.standard_normal((d, hidden)) * 0.6).astype(np.float32)
+    b0 = (rng.standard_normal(hidden) * 0.3).astype(np.float32)
+    W2 = (rng.standard_normal((hidden, u)) * 0.1).astype(np.float32)
+    b2 = (rng.standard_normal(u) * 0.1).astype(np.float32)
+    V = (0.01 * W0.astype(np.float64) @ W2.astype(np.float64)).astype(np.float32)
+    v0 = (b2.astype(np.float64) + 0.01 * b0.astype(np.float64) @ W2.astype(np.float64)).astype(np.float32)
+    Wc = (0.99 * W2.astype(np.float64)).astype(np.float32)
+    H32 = (y @ W0 + b0).astype(np.float32)
+    got = (y @ V + v0 + np.maximum(H32, np.float32(0)) @ Wc).astype(np.float64)
+    ref32 = (np.where(H32 > 0, H32, np.float32(0.01) * H32).astype(np.float32) @ W2 + b2).astype(np.float64)
+    H = y.astype(np.float64) @ W0.astype(np.float64) + b0
+    want = np.where(H > 0, H, 0.01 * H) @ W2.astype(np.float64) + b2
+    err, err32 = np.abs(got - want), np.abs(ref32 - want)
+    assert err.max() < 2e-6 and np.sqrt(np.mean(err ** 2)) < 1.5 * np.sqrt(np.mean(err32 ** 2)) + 1e-8
