@@ -403,8 +403,8 @@ def roofline_block(name, path, run, peaks, peak_kind):
         peak = float(peaks["hbm_gbs"])
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": (ach / peak) if ach else None,
-                # ncu --set full (profiles/r2_prof_acc_r2c_raw_summary.csv): dram read 8.0002 + write 0.0537 B per sample
-                "traffic": 8.0539 * n_local, "traffic_unit": "bytes per launch (ncu dram bytes/sample x samples)",
+                # ncu --set full (profiles/r2_prof_acc_r2e_raw_summary.csv): dram read 8.0002 + write 0.0510 B per sample
+                "traffic": 8.0512 * n_local, "traffic_unit": "bytes per launch (ncu dram bytes/sample x samples)",
                 "kernel": "accumulate_precomputed_kernel", "kernel_ms": kms,
                 "peak_source": "HBM copy bandwidth, of %s" % peak_kind}
     if name == "cfg4" and path != "simt":
@@ -412,9 +412,9 @@ def roofline_block(name, path, run, peaks, peak_kind):
         peak = float(peaks["bf16_tflops"]) / 2.0
         return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None,
-                # ncu --set full (profiles/r2_prof_tc_r2c_raw_summary.csv): 262.7 B of DRAM traffic per sample (read
-                # 260.2 + write 2.5; algorithmic 260 B): the kernel is not memory bound
-                "traffic": 262.7 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
+                # ncu --set full (profiles/r2_prof_tc_r2e_raw_summary.csv): 262.1 B of DRAM traffic per sample (read
+                # 260.2 + write 1.8; algorithmic 260 B): the kernel is not memory bound
+                "traffic": 262.1 * n_local, "traffic_unit": "DRAM bytes per launch (ncu bytes/sample x samples)",
                 "kernel": "realnvp_tc_kernel", "kernel_ms": kms,
                 "peak_source": "TF32 dense = bf16 burst / 2, of %s (the roofline BASELINE.json names; the kernel issues "
                                "kind::f16 MMAs, against the measured 16-bit peak the fraction is half of frac)" % peak_kind,
