@@ -798,6 +798,10 @@ realnvp_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* __
         ++pit;
         tc_fence_after();
         TR(9);
+#ifdef HB_TC_DELAY_NS  // experiment (profiles/README.md): an idle wait in every layer's serial chain -- is the kernel
+        // bound by the chain or by the power cap?
+        asm volatile("nanosleep.u32 %0;" ::"n"(HB_TC_DELAY_NS));
+#endif
         if (!scaled) {
           uint32_t v0[U], v1[8];
           tmem_ld32(tm_o - l, v0);
