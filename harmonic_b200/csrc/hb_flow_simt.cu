@@ -12,6 +12,8 @@
 
 #include "hb_internal.h"
 
+#include "hb_rqs.cuh"
+
 namespace hb {
 
 constexpr int FT = 128;  // threads per CTA = rows per tile
@@ -30,9 +32,6 @@ struct RealNVPSimtParams {
   SimtLayer layers[MAX_LAYERS];
 };
 
-__device__ __forceinline__ float softplus_acc(float a) {
-  return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a)));
-}
 
 // out[j] = act(b[j] + sum_i in[phys(i)] * W[i][j]); activations live in shared memory as
 // [feature][thread] columns; weights are read through the read-only path (warp-uniform
@@ -577,7 +576,6 @@ rqspline_simt_kernel(RQParams P, const XT* __restrict__ x, long long ld,
 // ------------------------------------------------------------------------------------------
 constexpr int RQF_THREADS = 128;
 constexpr int RQF_R = 2;
-constexpr int RQF_NP = 28;  // 3*8+1 = 25 spline parameters padded to 28
 
 struct RQFastParams {
   const float* pack;
@@ -586,84 +584,6 @@ struct RQFastParams {
   float lo, hi, T, sum_log_amp;
   int x_f64, lp_f64;
 };
-
-__device__ __forceinline__ float tanh_fast(float x) {
-  // tanh|x| = (1 - e) / (1 + e) with e = exp(-2|x|) in (0, 1] (MUFU ex2 / rcp): seven instructions.  The ABSOLUTE
-  // error is <= ~1.5e-7 everywhere (e carries 2^-22 relative, i.e. <= 2.4e-7 absolute, halved by the quotient's
-  // slope at 0); the relative error grows towards x = 0 (cancellation in 1 - e), which does not matter here: every
-  // tanh output only enters FMAs against the next Dense's weights and bias, where its absolute error counts like the
-  // rounding of any other O(1) float32 term (round 1 carried an odd series for |x| < 0.25 beside this: twice the
-  // instructions for no difference in ln phi at the 1e-7 level, profiles/README.md).
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * fabsf(x)));
-  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
-}
-
-// distrax RationalQuadraticSpline forward, K = 8, parameters in registers (static indexing only)
-__device__ __forceinline__ void rqs_forward_reg(float x, const float (&p)[RQF_NP], float lo, float hi,
-                                                float& yout, float& ldout) {
-  constexpr int K = 8;
-  const float mbs = 1e-4f, mks = 1e-4f;
-  const float off = 0.5411666523385311f;  // log(exp(1 - 1e-4) - 1)
-  const float span = (hi - lo) - (float)K * mbs;
-  float mw = p[0], mh = p[K];
-#pragma unroll
-  for (int k = 1; k < K; ++k) {
-    mw = fmaxf(mw, p[k]);
-    mh = fmaxf(mh, p[K + k]);
-  }
-  float ew[K], eh[K], sw = 0.f, shh = 0.f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    ew[k] = __expf(p[k] - mw);
-    eh[k] = __expf(p[K + k] - mh);
-    sw += ew[k];
-    shh += eh[k];
-  }
-  const float iw = span / sw, ih = span / shh;
-  float xl = lo, yl = lo, cw = 0.f, chh = 0.f;
-  float bxl = lo, bxr = lo, byl = lo, byr = lo, sl_raw = p[2 * K], sr_raw = p[2 * K + 1];
-  bool found = false;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    cw += fmaf(ew[k], iw, mbs);
-    chh += fmaf(eh[k], ih, mbs);
-    const float xr = (k == K - 1) ? hi : lo + cw;
-    const float yr = (k == K - 1) ? hi : lo + chh;
-    const bool in = (!found) && (x >= xl) && (x < xr);
-    if (k == 0 || in) {  // bin 0 is the default (e.g. NaN input)
-      bxl = xl; bxr = xr; byl = yl; byr = yr;
-      sl_raw = p[2 * K + k];
-      sr_raw = p[2 * K + k + 1];
-    }
-    found = found || in;
-    xl = xr;
-    yl = yr;
-  }
-  const bool below = x <= lo, above = x >= hi;
-  if (below) { sl_raw = p[2 * K]; }
-  if (above) { sl_raw = p[3 * K]; }
-  const float sl = softplus_acc(sl_raw + off) + mks;
-  const float sr = softplus_acc(sr_raw + off) + mks;
-  const float bw = bxr - bxl, bh = byr - byl;
-  const float delta = bh / bw;
-  float z = (x - bxl) / bw;
-  z = fminf(fmaxf(z, 0.f), 1.f);
-  if (x != x) z = x;  // jnp.clip propagates NaN
-  const float sq_z = z * z;
-  const float z1mz = z - sq_z;
-  const float omz = 1.f - z;
-  const float slopes_term = sr + sl - 2.f * delta;
-  const float numerator = bh * (delta * sq_z + sl * z1mz);
-  const float denominator = delta + slopes_term * z1mz;
-  float yv = byl + numerator / denominator;
-  float ldv = 2.f * __logf(delta) + __logf(sr * sq_z + 2.f * delta * z1mz + sl * omz * omz) -
-              2.f * __logf(denominator);
-  if (below) { yv = (x - lo) * sl + lo; ldv = __logf(sl); }
-  if (above) { yv = (x - hi) * sl + hi; ldv = __logf(sl); }
-  yout = yv;
-  ldout = ldv;
-}
 
 template <int D, bool FOLD>
 __global__ void __launch_bounds__(RQF_THREADS)
