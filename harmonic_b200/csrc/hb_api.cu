@@ -443,6 +443,7 @@ int hb_flow_destroy(hb_flow* h) {
   if (f->rq_pack) cudaFree(f->rq_pack);
   if (f->rqf_pack) cudaFree(f->rqf_pack);
   realnvp_tc_release(f);
+  rqspline_tc_release(f);
   realnvp_simt_release(f);
   realnvp_small_release(f);
   delete f;
@@ -467,7 +468,6 @@ int hb_flow_set_path(hb_flow* h, int path) {
 int hb_flow_uses_tcgen05(const hb_flow* h) {
   if (!h) return 0;
   const Flow* f = reinterpret_cast<const Flow*>(h);
-  if (f->desc.kind != HB_FLOW_REALNVP) return 0;
   return (f->path == HB_PATH_TCGEN05) || (f->path == HB_PATH_AUTO && f->tc_ok);
 }
 

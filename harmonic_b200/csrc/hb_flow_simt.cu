@@ -1272,7 +1272,9 @@ int rqspline_prepare(Flow* f) {
   HB_CUDA(cudaMemcpy(f->rq_pack, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
   f->rq_pack_floats = pack.size();
   f->rq_off.assign(1, lay_off);
-  return rqspline_fast_prepare(f);
+  const int rc = rqspline_fast_prepare(f);
+  if (rc) return rc;
+  return rqspline_tc_prepare(f);
 }
 
 // kernel parameters of the generic RQSpline kernels (log_prob and sampling direction)
@@ -1309,6 +1311,9 @@ int rqspline_run(Flow* f, float T, const void* x, int x_dtype, long long ld, lon
                  const int64_t* start, long long chain_lo, long long chain_hi, long long a,
                  long long b, cudaStream_t st) {
   if (n <= 0) return HB_OK;
+  if (f->path == HB_PATH_TCGEN05 || (f->path == HB_PATH_AUTO && f->rqtc))
+    return rqspline_tc_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start, chain_lo, chain_hi,
+                           a, b, st);
   if (f->rqf_pack && !f->force_generic)
     return rqspline_fast_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start, chain_lo,
                              chain_hi, a, b, st);

@@ -206,27 +206,6 @@ __device__ __forceinline__ void load_half<double>(const double* __restrict__ p, 
   }
 }
 
-// a - hs for the two halves of a packed FP16 pair hs and two float32 values (exact: hs is a rounded to 11 bits), by
-// one mixed-precision FMA each (FHFMA: hs * -1 + a); with ABS the float32 operands enter as |a|
-template <bool ABS>
-__device__ __forceinline__ void split_rest(uint32_t hs, float a0, float a1, float& l0, float& l1) {
-  const uint16_t m1 = 0xBC00;  // fp16(-1)
-  if (ABS) {
-    a0 = fabsf(a0);
-    a1 = fabsf(a1);
-  }
-  asm("{.reg .b16 a, b; mov.b32 {a, b}, %2; fma.rn.f32.f16 %0, a, %5, %3; fma.rn.f32.f16 %1, b, %5, %4;}"
-      : "=f"(l0), "=f"(l1)
-      : "r"(hs), "f"(a0), "f"(a1), "h"(m1));
-}
-// Split of a pair of conditioning inputs: hs = fp16(v) packed, lo = fp16(v - hs) packed
-__device__ __forceinline__ void split_x_pair(float va, float vb, uint32_t& hs, uint32_t& lo) {
-  hs = pack_f16x2(vb, va);
-  float la, lb;
-  split_rest<false>(hs, va, vb, la, lb);
-  lo = pack_f16x2(lb, la);
-}
-
 // E1 for one 16-column chunk of H: r = relu(H) as wh = 8 words of packed hs = fp16(r) pairs (rounded towards zero) and
 // wl = 8 words of packed fp16(r - hs) pairs.  Per pair: F2FP.RELU.RZ, 2 FHFMA, F2FP.RELU -- the clamp is part of the
 // conversions: for H < 0, hs = 0 and the "remainder" H - 0 < 0 is clamped by the second one; for H > 0 the remainder

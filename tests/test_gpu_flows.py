@@ -57,12 +57,17 @@ def test_realnvp_layer_counts_and_temperature(layers):
                                                  (3, (64, 64), 4), (5, (48, 16), 3), (8, (64, 64), 2),
                                                  (9, (32, 32), 2)])
 @pytest.mark.parametrize("standardize", [False, True])
-@pytest.mark.parametrize("path", [_lib.HB_PATH_AUTO, _lib.HB_PATH_SIMT_GENERIC])
+@pytest.mark.parametrize("path", [_lib.HB_PATH_AUTO, _lib.HB_PATH_SIMT, _lib.HB_PATH_SIMT_GENERIC])
 def test_rqspline_predict(ndim, hidden, layers, standardize, path):
-    """AUTO uses the register fast path for two hidden layers / ndim <= 8 / 8 bins and the generic
-    kernel otherwise; HB_PATH_SIMT_GENERIC forces the generic kernel."""
+    """AUTO uses the tcgen05 kernel at ndim 2 (two hidden layers, 32 / 64 wide, 8 bins), the register fast path for
+    two hidden layers / ndim <= 8 / 8 bins and the generic kernel otherwise; HB_PATH_SIMT keeps the CUDA-core kernels,
+    HB_PATH_SIMT_GENERIC forces the generic one."""
     if path == _lib.HB_PATH_SIMT_GENERIC and len(hidden) != 2:
         pytest.skip("generic kernel is already the AUTO choice")
+    if path == _lib.HB_PATH_SIMT and ndim != 2:
+        pytest.skip("AUTO is already the CUDA-core choice")
+    if path == _lib.HB_PATH_AUTO and ndim == 2:
+        pytest.skip("AUTO is the tensor path here: test_rqspline_tcgen05_*")
     m = util.make_rqspline(ndim, layers, 8, hidden, seed=ndim + layers, standardize=standardize)
     m.kernel_path = path
     x = samples(1500, ndim, seed=3, scale=2.0)
@@ -397,3 +402,116 @@ def test_realnvp_tcgen05_two_tile_layout():
     out = subprocess.run([sys.executable, "-c", _TWO_TILE_SCRIPT], cwd=root, env=env, capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0 and "two-tile ok" in out.stdout, out.stdout + out.stderr
+
+
+# ------------------------------------------------------------------ RQSpline on the tensor cores (ndim 2)
+@pytest.mark.parametrize("hidden,layers", [((64, 64), 8), ((32, 32), 3), ((64, 16), 5), ((32, 64), 1)])
+@pytest.mark.parametrize("standardize", [False, True])
+@pytest.mark.parametrize("n", [1, 127, 128, 1000, 70000])
+def test_rqspline_tcgen05_predict(hidden, layers, standardize, n):
+    """rqspline_tc_kernel (Dense(h1 -> 25) contraction as FP16-split tcgen05 MMAs) against the float64 oracle, at row
+    counts around the 128-sample tile and with samples in the spline's linear tails."""
+    m = util.make_rqspline(2, layers, 8, hidden, seed=layers + hidden[0], standardize=standardize, ws=0.3)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = samples(n, 2, seed=13, scale=2.0)
+    x[: n // 50] *= 8.0
+    got = m.predict(x)
+    assert _lib.load().hb_flow_uses_tcgen05(m._get_handle(0)) == 1
+    util.check_predict(m, x, got)
+    m2 = util.make_rqspline(2, layers, 8, hidden, seed=layers + hidden[0], standardize=standardize, ws=0.3)
+    m2.kernel_path = _lib.HB_PATH_SIMT
+    np.testing.assert_allclose(got, m2.predict(x), rtol=2e-5, atol=2e-5)
+
+
+def test_rqspline_tcgen05_ill_conditioned_flow_is_float32_grade():
+    """Weights of unit scale make the 8-layer flow ill-conditioned for ANY float32 evaluation (the float32 restatement of
+    the oracle itself leaves 1e-5 on ~0.3 % of the samples).  The tensor path must then be as good as float32 arithmetic
+    is: error statistics against the float64 oracle within a small factor of the CUDA-core kernel's and of the float32
+    restatement's -- per-sample slack proportional to ONE float32 evaluation's error would reject any other
+    float32-grade arithmetic on the samples where that evaluation happened to land close."""
+    m = util.make_rqspline(2, 8, 8, (64, 64), seed=10, standardize=True)
+    x = samples(40000, 2, seed=21, scale=2.0)
+    want = util.oracle_predict(m, x, np.float64)
+    den = np.maximum(np.abs(want), 1.0)
+    e32 = np.abs(util.oracle_predict(m, x, np.float32).astype(np.float64) - want) / den
+    errs = {}
+    for name, path in (("tc", _lib.HB_PATH_TCGEN05), ("simt", _lib.HB_PATH_SIMT)):
+        m.kernel_path = path
+        errs[name] = np.abs(np.asarray(m.predict(x), dtype=np.float64) - want) / den
+    ref_max = max(e32.max(), errs["simt"].max())
+    ref_cnt = max(int((e32 > 1e-5).sum()), int((errs["simt"] > 1e-5).sum()))
+    assert errs["tc"].max() <= 2.0 * ref_max
+    assert int((errs["tc"] > 1e-5).sum()) <= 1.5 * ref_cnt + 10
+    assert np.median(errs["tc"]) <= 1.5 * np.median(errs["simt"]) + 1e-8
+
+
+def test_rqspline_tcgen05_auto_and_unsupported_shapes():
+    lib = _lib.load()
+    m = util.make_rqspline(2, 8, 8, (64, 64), seed=2)
+    m.predict(samples(10, 2, seed=1))
+    assert lib.hb_flow_uses_tcgen05(m._get_handle(0)) == 1  # AUTO
+    for bad in (util.make_rqspline(3, 2, 8, (64, 64), seed=2), util.make_rqspline(2, 2, 8, (48, 16), seed=2),
+                util.make_rqspline(2, 2, 5, (64, 64), seed=2), util.make_rqspline(2, 2, 8, (64,), seed=2)):
+        bad.predict(samples(10, bad.ndim, seed=1))
+        assert lib.hb_flow_uses_tcgen05(bad._get_handle(0)) == 0
+        bad2 = util.make_rqspline(bad.ndim, 2, 8, (16, 16), seed=3)
+        bad2.kernel_path = _lib.HB_PATH_TCGEN05
+        with pytest.raises(Exception):
+            bad2.predict(samples(10, bad.ndim, seed=1))
+
+
+def test_rqspline_tcgen05_nan_and_inf_rows():
+    m = util.make_rqspline(2, 8, 8, (64, 64), seed=6, standardize=True, ws=0.3)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = samples(700, 2, seed=5)
+    x[3, 0] = np.nan
+    x[200, 1] = np.nan
+    x[9, 1] = np.inf
+    x[130, 0] = -np.inf
+    got = m.predict(x)
+    want = util.oracle_predict(m, x)
+    assert np.isnan(got[3]) and np.isnan(got[200])
+    keep = np.ones(700, bool)
+    keep[[9, 130]] = False
+    util.assert_lnphi_close(got[keep], want[keep])
+    assert not np.isfinite(got[9]) and not np.isfinite(got[130])
+
+
+@pytest.mark.parametrize("shift", [hm.Shifting.MEAN_SHIFT, hm.Shifting.MAX_SHIFT])
+def test_rqspline_tcgen05_fused_vs_oracle(shift):
+    """add_chains through the tensor-path kernel: ragged chains, two streaming calls, a NaN sample; equals the oracle
+    and the CUDA-core path."""
+    m = util.make_rqspline(2, 8, 8, (64, 64), seed=7, standardize=True, ws=0.3)
+    c1 = util.gaussian_chains(2, 14, 900, seed=1, ragged=True)
+    c2 = util.gaussian_chains(2, 14, 300, seed=2)
+    c2.samples[17, 1] = np.nan
+    ev = hm.Evidence(14, m, shift)
+    ev.add_chains(c1)
+    ev.add_chains(c2, num_slices=3)
+    ref = util.oracle_evidence(m, None, shift.value, calls=[c1, c2])
+    util.assert_evidence_close(ev, ref)
+    m2 = util.make_rqspline(2, 8, 8, (64, 64), seed=7, standardize=True, ws=0.3)
+    m2.kernel_path = _lib.HB_PATH_SIMT
+    ev2 = hm.Evidence(14, m2, shift)
+    ev2.add_chains(c1)
+    ev2.add_chains(c2, num_slices=3)
+    assert abs(ev.ln_evidence_inv - ev2.ln_evidence_inv) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_rqspline_tcgen05_device_strided_and_f64(dtype):
+    import torch
+    m = util.make_rqspline(2, 3, 8, (32, 32), seed=8, standardize=True, ws=0.3)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    n = 3000
+    big = torch.from_numpy(samples(n, 6, seed=36, scale=1.5)).to(getattr(torch, dtype)).cuda()
+    view = big[:, 2:4]
+    assert view.stride(0) == 6
+    got = m.predict(view).cpu().numpy()
+    util.check_predict(m, view.cpu().numpy().astype(np.float32 if dtype == "float32" else np.float64), got)
+    lnp = torch.from_numpy(np.random.default_rng(1).standard_normal(n)).to(getattr(torch, dtype)).cuda()
+    start = [0, 5, 900, 1300, 2100, n]
+    ev = hm.Evidence(5, m)
+    ev.add_chains(hm.Chains.from_arrays(view, lnp, start))
+    host = hm.Chains.from_arrays(view.cpu().numpy(), lnp.cpu().numpy(), start)
+    util.assert_evidence_close(ev, util.oracle_evidence(m, host))
