@@ -4,7 +4,7 @@
 // Per flow layer (harmonic/flows.py:234-288,335-438; App. A.2 of SURVEY.md) and sample, with v the conditioning feature
 // and t the transformed one (the mask alternates):
 //   a1 = tanh(Dense_0(where(mask, y, 0)))                      2 values,            CUDA cores
-//   a2 = tanh(Dense_1(a1))                                     h1 values,           CUDA cores (2 FMAs + a 7-instruction tanh)
+//   a2 = tanh(Dense_1(a1))                                     h1 values,           CUDA cores (2 FMAs + 6 instructions of a paired tanh)
 //   P  = c + a2 . M      M = last MLP Dense x output Dense     h1 x 25 contraction  TENSOR CORES
 //   y_t <- RationalQuadraticSpline(P)(y_t), then the scalar affine on both features                CUDA cores
 // M is formed on the host in float64 (no activation between the two Denses, flows.py:357,434-438).  The contraction is
@@ -53,8 +53,24 @@ constexpr int Q_BYTES = NP * 64 * 2;   // one K = 32 quarter: [32 x 64 K'], K' <
 constexpr uint32_t TM_A = 0, TM_P = MAXH, TM_TILE = MAXH + NP;
 static_assert(NT * TM_TILE <= 512, "TMEM");
 // float32 scalars of a layer: w1[2] b1[2] | scale[2] shift[2] | per hidden unit {W2[0][j], W2[1][j], b2[j], 0} | c[28]
+// (w1, b1, W2, b2 times 2 log2(e): tanh_pair_scaled)
 __host__ __device__ constexpr int scal_floats(int h1) { return 8 + 4 * h1 + RQF_NP; }
 constexpr int B_AFULL = 0, B_PFULL = NT, B_COUNT = 2 * NT;
+
+constexpr double TANH_ARG = 2.8853900817779268;  // 2 log2(e): both tanh Denses travel times this factor
+
+// tanh(x) from s = 2 log2(e) x (the factor sits in the Dense's weights and bias, host side): with e = 2^-|s| in (0, 1],
+// tanh|x| = (1 - e) / (1 + e) = 2 / (1 + e) - 1.  The kernel is bound by the MUFU pipe (ncu: 73 % busy at 2 MUFU per
+// tanh), so two hidden units share ONE reciprocal: R = 1 / ((1 + ea)(1 + eb)) -- the product stays in (1, 4] --,
+// 1 / (1 + ea) = (1 + eb) R.  Per pair 2 MUFU ex2 + 1 MUFU rcp + 9 other instructions.  Absolute error <= ~3e-7 (2^-22
+// relative on e, the reciprocal's ulp and two more roundings, halved by the quotient's slope), which is what the
+// consumers of a tanh output see (hb_rqs.cuh, tanh_fast).  s = +-inf gives +-1, NaN stays NaN.
+__device__ __forceinline__ void tanh_pair_scaled(float sa, float sb, float& ta, float& tb) {
+  const float da = ex2_approx(-fabsf(sa)) + 1.0f, db = ex2_approx(-fabsf(sb)) + 1.0f;
+  const float R = rcp_approx(da * db);
+  ta = copysignf(fmaf(2.0f, db * R, -1.0f), sa);
+  tb = copysignf(fmaf(2.0f, da * R, -1.0f), sb);
+}
 
 struct Params {
   const uint8_t* bimg;   // FP16 blocks: [layer][quarter] of Q_BYTES
@@ -190,8 +206,8 @@ rqspline_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* _
         const int par = li & 1;  // even layers: feature 1 conditions, feature 0 is transformed; odd layers the reverse
         const float yv = par ? y[0] : y[1];
         const float4 s0 = *reinterpret_cast<const float4*>(S);  // w1[v][0], w1[v][1], b1[0], b1[1]
-        const float a10 = tanh_fast(fmaf(yv, s0.x, s0.z));
-        const float a11 = tanh_fast(fmaf(yv, s0.y, s0.w));
+        float a10, a11;
+        tanh_pair_scaled(fmaf(yv, s0.x, s0.z), fmaf(yv, s0.y, s0.w), a10, a11);
         // ---- a2 = tanh(Dense_1(a1)) and its FP16 split, 16 hidden units per TMEM chunk
         const float4* W2 = reinterpret_cast<const float4*>(S + 8);
         for (int c = 0; c < (h1 >> 4); ++c) {
@@ -199,8 +215,8 @@ rqspline_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* _
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const float4 wa = W2[16 * c + 2 * jj], wb = W2[16 * c + 2 * jj + 1];
-            const float ta = tanh_fast(fmaf(a10, wa.x, fmaf(a11, wa.y, wa.z)));
-            const float tb2 = tanh_fast(fmaf(a10, wb.x, fmaf(a11, wb.y, wb.z)));
+            float ta, tb2;
+            tanh_pair_scaled(fmaf(a10, wa.x, fmaf(a11, wa.y, wa.z)), fmaf(a10, wb.x, fmaf(a11, wb.y, wb.z)), ta, tb2);
             split_x_pair(ta, tb2, wh[jj], wl[jj]);
           }
           tmem_st8(tm_a + 16 * c, wl);
@@ -228,7 +244,7 @@ rqspline_tc_kernel(Params P, const XT* __restrict__ x, long long ld, const LT* _
         }
         // ---- spline on the transformed feature, then the scalar affine on both
         float yo, lo_;
-        rqs_forward_reg(par ? y[1] : y[0], p, P.lo, P.hi, yo, lo_);
+        rqs_forward_mufu(par ? y[1] : y[0], p, P.lo, P.hi, yo, lo_);
         if (par) y[1] = yo; else y[0] = yo;
         ldet += lo_;
         const float4 s1 = *reinterpret_cast<const float4*>(S + 4);  // scale[2], shift[2]
@@ -306,18 +322,19 @@ int rqspline_tc_prepare(Flow* f) {
     const int par = i & 1;
     const int vis = par ? 0 : 1, tr = par ? 1 : 0;  // mask = (j % 2 == 1) on even layers, negated on odd ones
     float* S = scal.data() + (size_t)i * SF;
-    S[0] = W1[(size_t)vis * D + 0];
-    S[1] = W1[(size_t)vis * D + 1];
-    S[2] = b1[0];
-    S[3] = b1[1];
+    const double ta = rqtc::TANH_ARG;  // tanh_pair_scaled takes 2 log2(e) x
+    S[0] = (float)(ta * (double)W1[(size_t)vis * D + 0]);
+    S[1] = (float)(ta * (double)W1[(size_t)vis * D + 1]);
+    S[2] = (float)(ta * (double)b1[0]);
+    S[3] = (float)(ta * (double)b1[1]);
     S[4] = scales[0];
     S[5] = scales[1];
     S[6] = shifts[0];
     S[7] = shifts[1];
     for (int j = 0; j < h1; ++j) {
-      S[8 + 4 * j + 0] = W2[(size_t)0 * h1 + j];
-      S[8 + 4 * j + 1] = W2[(size_t)1 * h1 + j];
-      S[8 + 4 * j + 2] = b2[j];
+      S[8 + 4 * j + 0] = (float)(ta * (double)W2[(size_t)0 * h1 + j]);
+      S[8 + 4 * j + 1] = (float)(ta * (double)W2[(size_t)1 * h1 + j]);
+      S[8 + 4 * j + 2] = (float)(ta * (double)b2[j]);
     }
     float* cb = S + 8 + 4 * h1;
     for (int c = 0; c < npar; ++c) {
