@@ -420,6 +420,29 @@ def roofline_block(name, path, run, peaks, peak_kind):
                                "kind::f16 MMAs, against the measured 16-bit peak the fraction is half of frac)" % peak_kind,
                 "frac_of_16bit_peak": (ach / (2.0 * peak)) if ach else None,
                 "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
+    if name in ("cfg2", "cfg2x") and path != "simt":
+        # RQSpline at ndim 2: rqspline_tc_kernel.  The h1 x 25 contraction (93 % of the executed FLOPs) runs on the
+        # tensor cores as three FP16 MMAs per float32-equivalent product; what bounds the kernel is the CUDA cores'
+        # work around it -- two tanh layers (MUFU ex2 / rcp) and the spline -- so the fraction that says how close the
+        # kernel is to the hardware is the MUFU pipe's (16 results per clock and SM), beside the tensor-pipe figures.
+        # SURVEY.md 8(d) counts the reference's dense conditioner (all D rows of the (D, 3K+1) output, two separate
+        # last Denses); the kernel pre-multiplies the last two Denses (no activation between them,
+        # harmonic/flows.py:357,434-438) and evaluates only the transformed row, so it EXECUTES 4.3x fewer FLOPs.
+        L, h = (8, 64) if name == "cfg2" else (3, 32)
+        ex = L * 2.0 * (2 * 2 + 2 * h + h * 25)
+        mufu = L * (1.5 * (h + 2) + 25.0)  # per tanh pair 2 ex2 + 1 rcp; spline: 16 ex2, 6 rcp, 2 ex2 (softplus), 1 lg2
+        ach = wl.FLOP_PER_SAMPLE[name] * n_local / (kms * 1e-3) / 1e12 if kms else None
+        peak = float(peaks["bf16_tflops"]) / 2.0
+        mufu_peak = 148 * 16 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        return {"bound": "mufu", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": (mufu * n_local / (kms * 1e-3) / mufu_peak) if kms else None,
+                "frac_is": "MUFU results per second / (148 SMs x 16 per clock x max SM clock): the pipe that bounds it",
+                "frac_algorithmic_of_tf32": (ach / peak) if ach else None,
+                "frac_executed_of_tf32": (ach / peak * ex / wl.FLOP_PER_SAMPLE[name]) if ach else None,
+                "executed_flop_per_sample": ex, "mufu_per_sample": mufu,
+                "traffic": None, "kernel": "rqspline_tc_kernel", "kernel_ms": kms,
+                "peak_source": "TF32 dense = bf16 burst / 2, of %s; MUFU peak nominal" % peak_kind,
+                "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
     # small-ndim flows run on the FP32 CUDA cores (tensor tiles would be >= 75 % padding):
     # denominator = 148 SMs x 128 FMA lanes x 2 FLOP x max SM clock (nominal, not measured)
     ach = wl.FLOP_PER_SAMPLE[name] * n_local / (kms * 1e-3) / 1e12 if kms else None
@@ -431,11 +454,8 @@ def roofline_block(name, path, run, peaks, peak_kind):
             "peak_source": "FP32 CUDA-core FMA peak at the max SM clock (nominal)",
             "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
     if name in ("cfg2", "cfg2x") and ach:
-        # SURVEY.md 8(d) counts the reference's dense conditioner (all D rows of the (D, 3K+1) output, two
-        # separate last Denses).  The kernel pre-multiplies the last MLP Dense with the output Dense (no
-        # activation between them, harmonic/flows.py:357,434-438) and evaluates only the transformed rows,
-        # so it EXECUTES fewer FLOPs than the algorithmic count: the roofline fraction that means something
-        # is the executed one (the spline's MUFU work is not counted in either).
+        # the CUDA-core register kernel (--path simt): executed FLOPs against the FP32 FMA peak (the spline's MUFU
+        # work is not counted)
         L, h = (8, 64) if name == "cfg2" else (3, 32)
         ex = L * 2.0 * (2 * 2 + 2 * h + h * 25)
         roof["executed_flop_per_sample"] = ex
@@ -643,7 +663,7 @@ def main():
                "sample": "%d chains x %d samples (%.1f s) of the same workload, float32 restatement in oracle/"
                          % (cn, cp, dt)}
 
-    tc = name == "cfg4" and args.path != "simt"
+    tc = name in ("cfg4", "cfg2", "cfg2x") and args.path != "simt"
     line = {
         "metric": METRIC, "value": main_keep["value"], "unit": "samples/s", "n_gpus": ctx.world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": main_keep["ms_per_step"], "higher_is_better": True, "scaling": scaling,
