@@ -6,7 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("HB_BUILD_OUT") or os.path.join(HERE, "libharmonic_b200.so")  # HB_BUILD_OUT: variant builds
-SOURCES = ["hb_api.cu", "hb_accum.cu", "hb_flow_simt.cu", "hb_realnvp_tc.cu", "hb_rqspline_tc.cu"]
+SOURCES = ["hb_api.cu", "hb_accum.cu", "hb_flow_simt.cu", "hb_realnvp_tc.cu", "hb_rqspline_tc.cu",
+           "hb_realnvp_small_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -137,6 +137,9 @@ static int flow_run(Flow* f, float T, const void* x, int x_dtype, long long ld, 
     return rqspline_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start, chain_lo,
                         chain_hi, a, b, st);
   const bool tc = (f->path == HB_PATH_TCGEN05) || (f->path == HB_PATH_AUTO && f->tc_ok && !f->force_simt);
+  if (tc && f->stc)
+    return realnvp_small_tc_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start,
+                                chain_lo, chain_hi, a, b, f->tc_guard, st);
   if (tc)
     return realnvp_tc_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start,
                           chain_lo, chain_hi, a, b, f->tc_guard, st);
@@ -422,7 +425,8 @@ int hb_flow_create(const hb_flow_desc* ds, const float* weights, size_t n_weight
       set_error("RealNVP: ndim too large for the shared-memory activation layout (supported: ndim <= 163)");
       return HB_ERR_UNSUPPORTED;
     }
-    rc = realnvp_tc_prepare(f);  // sets tc_ok when the shape is supported
+    rc = realnvp_tc_prepare(f);  // sets tc_ok when the shape is supported (ndim 64)
+    if (!rc) rc = realnvp_small_tc_prepare(f);  // ndim 2..8
   } else {
     rc = rqspline_prepare(f);
   }
@@ -443,6 +447,7 @@ int hb_flow_destroy(hb_flow* h) {
   if (f->rq_pack) cudaFree(f->rq_pack);
   if (f->rqf_pack) cudaFree(f->rqf_pack);
   realnvp_tc_release(f);
+  realnvp_small_tc_release(f);
   rqspline_tc_release(f);
   realnvp_simt_release(f);
   realnvp_small_release(f);

@@ -126,6 +126,7 @@ struct Flow {
   void* tc_image = nullptr;
   size_t tc_image_bytes = 0;
   bool tc_ok = false;
+  void* stc = nullptr;   // small-ndim RealNVP tcgen05 path: resident weight image (hb_realnvp_small_tc.cu); sets tc_ok
   void* rqtc = nullptr;  // RQSpline tcgen05 path: resident weight image (hb_rqspline_tc.cu); sets tc_ok
   // range guard of the tensor path (hb_realnvp_tc.cu): device counter of rows beyond the limits since the last
   // hb_flow_guard_take, and the limits on |standardised input| / |any conditioning input|
@@ -153,6 +154,12 @@ int realnvp_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, l
 int flow_sample_run(Flow* f, float T, const void* eps, int eps_dtype, long long ld, long long n, float* out,
                     long long ldo, cudaStream_t st);
 int realnvp_tc_prepare(Flow* f);  // builds tc_image; sets tc_ok
+int realnvp_small_tc_prepare(Flow* f);  // builds stc for ndim 2..8; sets tc_ok, allocates tc_guard
+void realnvp_small_tc_release(Flow* f);
+int realnvp_small_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
+                         const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
+                         const int64_t* start, long long chain_lo, long long chain_hi, long long a,
+                         long long b, unsigned long long* guard, cudaStream_t st);
 int rqspline_tc_prepare(Flow* f);  // builds rqtc for the shapes the RQSpline tensor path serves; sets tc_ok
 void rqspline_tc_release(Flow* f);
 int rqspline_tc_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,

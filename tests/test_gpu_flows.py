@@ -515,3 +515,85 @@ def test_rqspline_tcgen05_device_strided_and_f64(dtype):
     ev.add_chains(hm.Chains.from_arrays(view, lnp, start))
     host = hm.Chains.from_arrays(view.cpu().numpy(), lnp.cpu().numpy(), start)
     util.assert_evidence_close(ev, util.oracle_evidence(m, host))
+
+
+# ------------------------------------------------------------------ small-ndim RealNVP on the tensor cores (ndim 2..8)
+@pytest.mark.parametrize("ndim", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("standardize", [False, True])
+@pytest.mark.parametrize("layers", [(2, 4), (6, 2), (1, 3)])
+def test_realnvp_small_tcgen05_predict(ndim, standardize, layers):
+    """realnvp_small_tc_kernel (relu(H) (0.99 W2) as FP16-split tcgen05 MMAs, H and the linear part on the CUDA cores)
+    against the float64 oracle and the register kernel."""
+    m = util.make_realnvp(ndim, layers[0], layers[1], seed=ndim + 3 * layers[0], standardize=standardize, ws=0.3)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = samples(3000, ndim, seed=7, scale=1.5)
+    got = m.predict(x)
+    assert _lib.load().hb_flow_uses_tcgen05(m._get_handle(0)) == 1
+    util.check_predict(m, x, got)
+    m2 = util.make_realnvp(ndim, layers[0], layers[1], seed=ndim + 3 * layers[0], standardize=standardize, ws=0.3)
+    m2.kernel_path = _lib.HB_PATH_SIMT
+    np.testing.assert_allclose(got, m2.predict(x), rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 50000])
+def test_realnvp_small_tcgen05_row_counts_and_auto(n):
+    m = util.make_realnvp(5, 6, 2, seed=3, standardize=True, ws=0.3)  # the cfg3 flow; AUTO = tensor path
+    x = samples(n, 5, seed=2)
+    got = m.predict(x)
+    assert _lib.load().hb_flow_uses_tcgen05(m._get_handle(0)) == 1
+    util.check_predict(m, x, got)
+
+
+def test_realnvp_small_tcgen05_nan_inf_and_guard(caplog):
+    """NaN rows propagate, an infinite feature never gives a finite ln phi; rows far outside the range where
+    fp16(relu(h)) is finite trip the guard: AUTO evaluates the call again on the CUDA cores and says so, the forced
+    tensor path does not."""
+    import logging
+    m = util.make_realnvp(5, 6, 2, seed=3, standardize=True, ws=0.3)
+    x = samples(600, 5, seed=5)
+    x[3, 0] = np.nan
+    x[7, 4] = np.nan
+    x[9, 1] = np.inf
+    got = m.predict(x)
+    want = util.oracle_predict(m, x)
+    assert np.isnan(got[3]) and np.isnan(got[7]) and not np.isfinite(got[9])
+    util.assert_lnphi_close(np.delete(got, 9), np.delete(want, 9))
+    far = samples(600, 5, seed=6)
+    far[11, 2] = 3.0e6
+    with caplog.at_level(logging.WARNING, logger="Harmonic"):
+        got = m.predict(far)
+    assert any("CUDA cores" in r.message for r in caplog.records)
+    m2 = util.make_realnvp(5, 6, 2, seed=3, standardize=True, ws=0.3)
+    m2.kernel_path = _lib.HB_PATH_SIMT
+    np.testing.assert_array_equal(got, m2.predict(far))  # the re-evaluation IS the CUDA-core path
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_realnvp_small_tcgen05_fused_vs_oracle(dtype):
+    """add_chains through the tensor-path kernel: ragged chains, two streaming calls, a NaN sample, host float64 and
+    device-resident strided inputs; equals the oracle and the register kernel."""
+    import torch
+    m = util.make_realnvp(5, 6, 2, seed=2, standardize=True, ws=0.3)
+    c1 = util.gaussian_chains(5, 14, 900, seed=1, ragged=True)
+    c2 = util.gaussian_chains(5, 14, 300, seed=2)
+    c2.samples[17, 1] = np.nan
+    ev = hm.Evidence(14, m)
+    ev.add_chains(c1)
+    ev.add_chains(c2, num_slices=3)
+    ref = util.oracle_evidence(m, None, calls=[c1, c2])
+    util.assert_evidence_close(ev, ref)
+    m2 = util.make_realnvp(5, 6, 2, seed=2, standardize=True, ws=0.3)
+    m2.kernel_path = _lib.HB_PATH_SIMT
+    ev2 = hm.Evidence(14, m2)
+    ev2.add_chains(c1)
+    ev2.add_chains(c2, num_slices=3)
+    assert abs(ev.ln_evidence_inv - ev2.ln_evidence_inv) < 1e-5
+    n = 3000
+    big = torch.from_numpy(samples(n, 9, seed=36)).to(getattr(torch, dtype)).cuda()
+    view = big[:, 2:7]
+    lnp = torch.from_numpy(np.random.default_rng(1).standard_normal(n)).to(getattr(torch, dtype)).cuda()
+    start = [0, 5, 900, 1300, 2100, n]
+    ev3 = hm.Evidence(5, m)
+    ev3.add_chains(hm.Chains.from_arrays(view, lnp, start))
+    host = hm.Chains.from_arrays(view.cpu().numpy(), lnp.cpu().numpy(), start)
+    util.assert_evidence_close(ev3, util.oracle_evidence(m, host))
