@@ -420,6 +420,21 @@ def roofline_block(name, path, run, peaks, peak_kind):
                                "kind::f16 MMAs, against the measured 16-bit peak the fraction is half of frac)" % peak_kind,
                 "frac_of_16bit_peak": (ach / (2.0 * peak)) if ach else None,
                 "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
+    if name == "cfg3" and path != "simt":
+        # RealNVP at ndim 5 with >= 2^20 rows per call: realnvp_small_tc_kernel, both contractions of the coupling MLP on
+        # the tensor cores (three FP16 MMAs per float32-equivalent product).  Tiles are 90 % padding at this shape (K = 16
+        # for d + 1 = 3 inputs, N = 16 for 2u = 6 outputs), so the tensor-pipe fraction says little; the figure beside
+        # it is the algorithmic FLOP rate against what the FP32 CUDA cores could deliver at most (> 1 means the kernel
+        # is beyond any CUDA-core implementation's reach).
+        ach = wl.FLOP_PER_SAMPLE[name] * n_local / (kms * 1e-3) / 1e12 if kms else None
+        peak = float(peaks["bf16_tflops"]) / 2.0
+        fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": (ach / peak) if ach else None,
+                "frac_of_fp32_cuda_core_peak": (ach / fp32_peak) if ach else None,
+                "traffic": None, "kernel": "realnvp_small_tc_kernel", "kernel_ms": kms,
+                "peak_source": "TF32 dense = bf16 burst / 2, of %s; FP32 CUDA-core peak nominal" % peak_kind,
+                "algorithmic_flop_per_sample": wl.FLOP_PER_SAMPLE[name]}
     if name in ("cfg2", "cfg2x") and path != "simt":
         # RQSpline at ndim 2: rqspline_tc_kernel.  The h1 x 25 contraction (93 % of the executed FLOPs) runs on the
         # tensor cores as three FP16 MMAs per float32-equivalent product; what bounds the kernel is the CUDA cores'
@@ -663,7 +678,7 @@ def main():
                "sample": "%d chains x %d samples (%.1f s) of the same workload, float32 restatement in oracle/"
                          % (cn, cp, dt)}
 
-    tc = name in ("cfg4", "cfg2", "cfg2x") and args.path != "simt"
+    tc = name in ("cfg4", "cfg3", "cfg2", "cfg2x") and args.path != "simt"
     line = {
         "metric": METRIC, "value": main_keep["value"], "unit": "samples/s", "n_gpus": ctx.world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": main_keep["ms_per_step"], "higher_is_better": True, "scaling": scaling,

@@ -129,6 +129,23 @@ int ensure_stage(Stage* acc, size_t bytes_per_slot) {
 
 static int round_half_even_half(int ndim) { return (int)nearbyint(ndim * 0.5); }
 
+// Small-ndim RealNVP under HB_PATH_AUTO: the tensor path's range guard ends every call with a device-to-host read of its
+// counter (~30 us); below this many rows that costs more than realnvp_small_tc_kernel saves over the register kernel
+// (cfg1, 5e5 rows: kernel 0.16 -> 0.10 ms, whole step 0.31 -> 0.34 ms).  HB_STC_MIN_ROWS overrides (tests: 0).
+static long long stc_min_rows() {
+  static const long long v = [] {
+    const char* e = getenv("HB_STC_MIN_ROWS");
+    return e ? atoll(e) : (long long)1 << 20;
+  }();
+  return v;
+}
+
+static bool use_tc(const Flow* f, long long n) {
+  if (f->path == HB_PATH_TCGEN05) return true;
+  if (!(f->path == HB_PATH_AUTO && f->tc_ok && !f->force_simt)) return false;
+  return !(f->stc && n < stc_min_rows());
+}
+
 static int flow_run(Flow* f, float T, const void* x, int x_dtype, long long ld, long long n,
                     const void* lnpost, int lp_dtype, float* lnpred_out, Accum* acc,
                     const int64_t* start, long long chain_lo, long long chain_hi, long long a,
@@ -136,7 +153,7 @@ static int flow_run(Flow* f, float T, const void* x, int x_dtype, long long ld, 
   if (f->desc.kind == HB_FLOW_RQSPLINE)
     return rqspline_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start, chain_lo,
                         chain_hi, a, b, st);
-  const bool tc = (f->path == HB_PATH_TCGEN05) || (f->path == HB_PATH_AUTO && f->tc_ok && !f->force_simt);
+  const bool tc = use_tc(f, n);
   if (tc && f->stc)
     return realnvp_small_tc_run(f, T, x, x_dtype, ld, n, lnpost, lp_dtype, lnpred_out, acc, start,
                                 chain_lo, chain_hi, a, b, f->tc_guard, st);
@@ -149,8 +166,8 @@ static int flow_run(Flow* f, float T, const void* x, int x_dtype, long long ld, 
 
 // Range guard of the tensor path (hb_realnvp_tc.cu): under HB_PATH_AUTO a call whose rows left the range the
 // FP16-split arithmetic serves is evaluated again on the CUDA cores (float32 FMA arithmetic, any magnitude).
-static bool guarded(const Flow* f) {
-  return f->desc.kind == HB_FLOW_REALNVP && f->path == HB_PATH_AUTO && f->tc_ok && !f->force_simt && f->tc_guard;
+static bool guarded(const Flow* f, long long n) {
+  return f->desc.kind == HB_FLOW_REALNVP && f->path == HB_PATH_AUTO && f->tc_guard && use_tc(f, n);
 }
 // rows counted since the last take; stream-ordered read + reset, then waits for the stream
 static int guard_take(Flow* f, cudaStream_t st, long long* count) {
@@ -491,7 +508,7 @@ int hb_flow_predict(hb_flow* h, float temperature, const void* x, int x_dtype, i
   HB_REQUIRE(x != nullptr && out != nullptr, "NULL buffer");
   HB_CUDA(cudaSetDevice(f->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool guard = guarded(f);
+  const bool guard = guarded(f, n);
   int rc = flow_predict_once(f, temperature, x, x_dtype, x_mem, n, ld, out, out_mem, st);
   if (rc || !guard) return rc;
   long long cnt = 0;
@@ -631,7 +648,7 @@ int hb_accumulate_flow(hb_accum* ha, hb_flow* hf, float temperature, const void*
   if (rc) return rc;
   if (!has_rows) return HB_OK;
   HB_REQUIRE(x != nullptr && ln_posterior != nullptr, "NULL input buffer");
-  if (!guarded(f))
+  if (!guarded(f, nrows))
     return accumulate_flow_once(acc, f, temperature, x, x_dtype, ld, ln_posterior, lp_dtype, mem, start_indices,
                                 chain_lo, chain_hi, nrows, lnpred_out, st);
   // guarded call: keep a copy of the (small) state block so that the call can be folded again on the CUDA cores

@@ -1,32 +1,33 @@
-// RealNVP log_prob (+ fused harmonic-mean fold) for small ndim (2..8) with the coupling MLP's second contraction on the
-// tcgen05 tensor cores (harmonic/flows.py:41-116,159-180; the Pima-Indian example and BASELINE cfg3 are ndim 5).
+// RealNVP log_prob (+ fused harmonic-mean fold) for small ndim (2..8) with BOTH contractions of the coupling MLP on the
+// tcgen05 tensor cores (harmonic/flows.py:41-116,159-180; the Pima-Indian example and BASELINE cfg3 are ndim 5) -- the
+// structure of hb_realnvp_tc.cu in miniature, with all weights resident in shared memory.
 //
-// A coupling layer conditions on d = round(ndim / 2) features and has a fixed hidden width of 128 (flows.py:171):
-//   H = y0 W0 + b0                         128 x d FMAs per sample: too thin for a GEMM, CUDA cores
-//   [shift | scale pre-activation] = leaky_relu(H) [Wt | Ws] + [bt | bs]     128 x 2u: K = 128, N <= 8 -> TENSOR CORES
-// With leaky_relu(h) = s h + c relu(h) (s = 0.01, c = 0.99) the linear part s (y0 W0 + b0) W2 + b2 = y0 V + v0 is a
-// d x 2u matrix formed once on the host in float64 (as in realnvp_small_kernel) and the contraction that remains is
-// relu(H) (c W2).  It runs as the three-product FP16 split of hb_realnvp_tc.cu: r = relu(h) as
-// hs = fp16(r) rounded towards zero and lo = fp16(r - hs), both by conversions whose clamp is a modifier
-// (cvt.rz.relu / cvt.rn.relu) and one mixed-precision FMA per element; c W2 = w_hi + w_lo travelling times 2^5;
-// tcgen05.mma kind::f16, M = 128 samples, N = 16, A from TMEM, FP32 accumulation.  On the CUDA cores
-// (realnvp_small_kernel) the contraction is 6 of the ~9.75 instructions per hidden unit and sample of a scaled ndim-5
-// layer; here a hidden unit costs d FMAs, 2 instructions of the split and one LDS.
+// A coupling layer conditions on d = round(ndim / 2) <= 4 features and has a fixed hidden width of 128 (flows.py:171):
+//   GEMM1  H = y0 W0 + b0                      ONE MMA: the three products of the FP16 split and the bias fit a single K = 16
+//                                              operand,  A = [hs(y0) 0.. | 1 | lo(y0) 0.. | 0 | hs(y0) 0.. | 1 | 0]  (shared memory),
+//                                              B rows  = [w_hi      | b_hi | w_hi      | 0 | w_lo      | b_lo | 0],  N = 128
+//   E1     r = relu(H) -> FP16 pair (hs, r - hs) in place of H: conversions whose clamp is a modifier (cvt.rz.relu /
+//          cvt.rn.relu) and one mixed-precision FMA per element, 16 columns per step
+//   GEMM2  O[128 x 16] = relu(H) (c W2), c = 0.99: per K = 32 quarter 6 MMAs (A from TMEM), issued while E1 works on the
+//          next quarter
+//   E2     leaky_relu(h) = s h + c relu(h): the linear part s (y0 W0 + b0) W2 + b2 = y0 V + v0 (a d x 2u matrix formed on
+//          the host in float64, as in realnvp_small_kernel) is evaluated in registers while GEMM1 runs; shift, softplus-clip
+//          scale, log-det as in the ndim-64 kernel's E2
+// Weights travel times 2^5 (so that the lo halves stay normal halves): H accumulates 2^5, O 2^10 times its value.  The
+// first version of this kernel computed H on the CUDA cores from per-hidden-unit records in shared memory: one sample per
+// thread (TMEM lane = sample) leaves nothing to amortise the records over, and the loop was bound by shared-memory
+// wavefronts (ncu: 75 % of the cycles; profiles/README.md).  Here a hidden unit costs the CUDA cores two instructions.
 //
-// Range: hs = fp16(relu(h)) needs h < 65504.  |h| <= max_j sum_i |W0[i][j]| max|y0| + max|b0|; every epilogue thread
+// Range: hs = fp16(2^5 relu(h)) needs h < 2047 (|h| <= max_j sum_i |W0[i][j]| max|y0| + max|b0|), and far outside the trained
+// range (conditioning inputs beyond ~128 units; the limit is 64) the truncating accumulator costs accuracy.  Every epilogue thread
 // tracks max |conditioning input| of its row over the layers, rows beyond the limit derived at flow creation are
 // counted into the flow's guard counter and HB_PATH_AUTO answers by evaluating the call again on the CUDA cores
-// (hb_api.cu, as for the ndim-64 kernel).  NaN inputs do not trip the guard: they propagate (relu(NaN) stays NaN in
-// both conversions).
+// (hb_api.cu, as for the ndim-64 kernel).  NaN inputs do not trip the guard: they propagate.
 //
-// One persistent CTA per SM: four epilogue warpgroups, each owning one 128-sample tile (TMEM lane = sample), and one
-// auxiliary warpgroup whose warp t issues tile t's 24 MMAs per layer.  All layers' weights are resident in shared memory
-// (8 KiB of FP16 blocks + 2-4 KiB of float32 records per layer).  Seven mbarriers per tile: one per K = 32 quarter of A (the
-// quarter's 6 MMAs run while the epilogue computes the next one), two "buffer free" commits and OFULL (tcgen05.commit after the
-// last quarter).
-// TMEM per tile (80 columns): A (two K = 32 quarter buffers of 32 columns: per 16 hidden units 8 columns of packed lo pairs + 8
-// of packed hs pairs; quarters 2 / 3 reuse the buffers of quarters 0 / 1 once their MMAs have completed -- with all four
-// quarters resident only three tiles fit TMEM, and three warps per scheduler left the issue slots 39 % idle) | O (16).
+// One persistent CTA per SM: three epilogue warpgroups, each owning one 128-sample tile (TMEM lane = sample), and one
+// auxiliary warpgroup whose warp t issues tile t's 25 MMAs per layer.  Shared memory: 12 KiB of FP16 blocks per layer, 4 KiB
+// of A operand per tile.  Seven mbarriers per tile: A1FULL / HFULL around GEMM1, one per quarter of E1, OFULL.
+// TMEM per tile (144 columns): P (128: H, then per 16-column chunk 8 columns of packed lo pairs + 8 of packed hs pairs) | O (16).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,25 +44,23 @@ namespace stc {
 using namespace tcx;
 
 constexpr int TILE = 128;
-constexpr int NT = 4;
+constexpr int NT = 3;
 constexpr int THREADS = NT * 128 + 128;
 constexpr int HID = 128;
-constexpr int NO = 16;                  // GEMM N: 2u <= 8 outputs padded to 16
-constexpr float SU = 32.0f, SU_INV = 1.0f / SU;
-constexpr int Q_BYTES = NO * 64 * 2;    // one K = 32 quarter: [16 x 64 K'], K' < 32 w_hi, K' >= 32 w_lo
-constexpr int L_BYTES = 4 * Q_BYTES;    // per layer
-constexpr uint32_t TM_A = 0, TM_O = 64, TM_TILE = 64 + NO;  // A: two K = 32 quarter buffers (quarter q lives in buffer q & 1)
+constexpr int NO = 16;                  // GEMM2 N: 2u <= 8 outputs padded to 16
+constexpr float SH = 32.0f, SU = 32.0f, SO_INV = 1.0f / (SH * SU);
+constexpr int G1_BYTES = HID * 16 * 2;  // GEMM1 block [128 x 16 K']
+constexpr int Q_BYTES = NO * 64 * 2;    // one K = 32 quarter of GEMM2: [16 x 64 K'], K' < 32 w_hi, K' >= 32 w_lo
+constexpr int L_BYTES = G1_BYTES + 4 * Q_BYTES;  // per layer
+constexpr int A1_BYTES = TILE * 16 * 2;  // GEMM1 A operand of a tile
+constexpr uint32_t TM_P = 0, TM_O = HID, TM_TILE = HID + NO;
 static_assert(NT * TM_TILE <= 512, "TMEM");
-constexpr int B_AQ = 0 /* [quarter][tile]: one K = 32 quarter of A has been written */,
-              B_QD = 4 * NT /* [buffer][tile]: the MMAs of quarter 0 / 1 have completed, the buffer may be rewritten */,
-              B_OFULL = 6 * NT, B_COUNT = 7 * NT;
+constexpr int B_A1FULL = 0, B_HFULL = NT, B_AQ = 2 * NT /* [quarter][tile] */, B_OFULL = 6 * NT, B_COUNT = 7 * NT;
+// K' slots of the GEMM1 operand
+constexpr int K_HS = 0, K_ONE = 4, K_LO = 5, K_HS2 = 10, K_ONE2 = 14;
 __host__ __device__ constexpr int small_d(int D) { return (D == 2) ? 1 : (D == 3) ? 2 : (D == 4) ? 2 : (D == 5) ? 2 : (D == 6) ? 3 : 4; }
-__host__ __device__ constexpr int rec_floats(int D) { return 1 + small_d(D); }  // {b0[j], W0[0..d-1][j]}, unpadded: four
-// records are (1 + d) LDS.128 (shared-memory wavefronts bound this loop, profiles/README.md)
-// float32 block of a layer: 128 records, then the linear part: (1 + d) rows of 2 x (4-padded u) floats
-__host__ __device__ constexpr int scal_floats(int D) {
-  return HID * rec_floats(D) + (1 + small_d(D)) * 2 * (((D - small_d(D)) + 3) & ~3);
-}
+// float32 block of a layer: the linear part, (1 + d) rows of 2 x (4-padded u) floats
+__host__ __device__ constexpr int scal_floats(int D) { return (1 + small_d(D)) * 2 * (((D - small_d(D)) + 3) & ~3); }
 
 struct Params {
   const uint8_t* bimg;  // [layer] of L_BYTES
@@ -86,18 +85,33 @@ __device__ __forceinline__ float softplus_clip_fast(float a) {
   return fminf(fmaxf(fmaf(uu + uu, p, fmaxf(a, 0.f)), 1e-3f), 1e3f);
 }
 
+// E1 for one 16-column chunk of H (hb_realnvp_tc.cu, e1_chunk): wh = 8 words of packed hs = fp16(relu(H)) pairs rounded
+// towards zero, wl = 8 words of packed fp16(relu(H) - hs) pairs
+__device__ __forceinline__ void e1_chunk(const uint32_t (&v)[16], uint32_t (&wl)[8], uint32_t (&wh)[8]) {
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const float h0 = __uint_as_float(v[2 * jj]), h1 = __uint_as_float(v[2 * jj + 1]);
+    const uint32_t hs = pack_relu_rz_f16x2(h1, h0);
+    float l0, l1;
+    split_rest<false>(hs, h0, h1, l0, l1);
+    wh[jj] = hs;
+    wl[jj] = pack_relu_f16x2(l1, l0);
+  }
+}
+
 template <int D, bool FOLD>
 __global__ void __launch_bounds__(THREADS, 1)
 realnvp_small_tc_kernel(Params P, const void* __restrict__ xv, long long ld, const void* __restrict__ lnpostv,
                         float* __restrict__ lnpred_out, FoldParams fp) {
-  constexpr int d = small_d(D), u = D - d, UP = (u + 3) & ~3, RF = rec_floats(D), SF = scal_floats(D);
+  constexpr int d = small_d(D), u = D - d, UP = (u + 3) & ~3, SF = scal_floats(D);
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int nl = P.nlayers;
   const uint32_t img_bytes = (uint32_t)nl * L_BYTES;
   uint8_t* s_img = smem;
-  float* s_scal = reinterpret_cast<float*>(smem + img_bytes);
-  uint8_t* s_tail = smem + img_bytes + (((uint32_t)nl * SF * 4 + 15) & ~15u);
+  uint8_t* s_a1 = smem + img_bytes;
+  float* s_scal = reinterpret_cast<float*>(s_a1 + NT * A1_BYTES);
+  uint8_t* s_tail = reinterpret_cast<uint8_t*>(s_scal) + (((uint32_t)nl * SF * 4 + 15) & ~15u);
   const uint32_t bar0 = smem_u32(s_tail);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(s_tail + 8 * B_COUNT);
@@ -105,8 +119,9 @@ realnvp_small_tc_kernel(Params P, const void* __restrict__ xv, long long ld, con
 
   if (threadIdx.x == 0) {
     for (int t = 0; t < NT; ++t) {
+      mbar_init(BAR(B_A1FULL + t), 128);
+      mbar_init(BAR(B_HFULL + t), 1);
       for (int q = 0; q < 4; ++q) mbar_init(BAR(B_AQ + NT * q + t), 128);
-      for (int q = 0; q < 2; ++q) mbar_init(BAR(B_QD + NT * q + t), 1);
       mbar_init(BAR(B_OFULL + t), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -131,32 +146,43 @@ realnvp_small_tc_kernel(Params P, const void* __restrict__ xv, long long ld, con
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp >= NT * 4) {
-    // ===== MMA issuers: warp NT * 4 + t serves tile t =====
+    // ===== MMA issuers: warp NT * 4 + t serves tile t; the whole warp runs the loop, one elected lane issues =====
     const int t = warp - NT * 4;
     if (t < NT) {
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + t * TM_TILE;
-      const uint32_t idesc = make_idesc_f16(NO);
-      const uint32_t lbo = NO * 16;
-      const uint64_t kstep = (uint64_t)((2 * lbo) >> 4);
+      const uint32_t ih = make_idesc_f16(HID), io = make_idesc_f16(NO);
+      const uint32_t lbo2 = NO * 16;
+      const uint64_t kstep = (uint64_t)((2 * lbo2) >> 4);
       const uint32_t img0 = smem_u32(s_img);
+      const uint64_t adesc = make_desc(smem_u32(s_a1) + (uint32_t)t * A1_BYTES, TILE * 16, 128);
       uint32_t it = 0;
       for (int b = 0; b < P.nbatches; ++b) {
         for (int l = 0; l < nl; ++l, ++it) {
+          const uint32_t lay = img0 + (uint32_t)l * L_BYTES;
+          // ---- GEMM1: one MMA
+          mbar_wait(BAR(B_A1FULL + t), it & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            mma_ss_f16(tb + TM_P, adesc, make_desc(lay, HID * 16, 128), ih, 0);
+            tc_commit(BAR(B_HFULL + t));
+          }
+          __syncwarp();
+          // ---- GEMM2: quarter q as soon as E1 has written it
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {  // quarter q as soon as the epilogue has written it: the MMAs run under the
-            mbar_wait(BAR(B_AQ + NT * q + t), it & 1);  // epilogue's work on quarter q + 1
+          for (int q = 0; q < 4; ++q) {
+            mbar_wait(BAR(B_AQ + NT * q + t), it & 1);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t bd = make_desc(img0 + (uint32_t)l * L_BYTES + (uint32_t)q * Q_BYTES, lbo, 128);
-              const uint32_t a0 = tb + TM_A + 32 * (q & 1);
+              const uint64_t bd = make_desc(lay + G1_BYTES + (uint32_t)q * Q_BYTES, lbo2, 128);
+              const uint32_t a0 = tb + TM_P + 32 * q;
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
                 const uint32_t a_lo = a0 + 16 * half, a_hs = a_lo + 8;
-                mma_ts_f16(tb + TM_O, a_lo, bd + (uint64_t)half * kstep, idesc, (q | half) ? 1u : 0u);
-                mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(2 + half) * kstep, idesc, 1);
-                mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)half * kstep, idesc, 1);
+                // small terms first (lo . w_hi, hs . w_lo), then the main term hs . w_hi
+                mma_ts_f16(tb + TM_O, a_lo, bd + (uint64_t)half * kstep, io, (q | half) ? 1u : 0u);
+                mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)(2 + half) * kstep, io, 1);
+                mma_ts_f16(tb + TM_O, a_hs, bd + (uint64_t)half * kstep, io, 1);
               }
-              if (q < 2) tc_commit(BAR(B_QD + NT * q + t));
               if (q == 3) tc_commit(BAR(B_OFULL + t));
             }
             __syncwarp();
@@ -169,8 +195,9 @@ realnvp_small_tc_kernel(Params P, const void* __restrict__ xv, long long ld, con
     const int wg = warp >> 2;
     const int tid = threadIdx.x & 127;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    const uint32_t tm_a = tmem_base + lane_base + wg * TM_TILE + TM_A;
+    const uint32_t tm_p = tmem_base + lane_base + wg * TM_TILE + TM_P;
     const uint32_t tm_o = tmem_base + lane_base + wg * TM_TILE + TM_O;
+    uint8_t* a1 = s_a1 + wg * A1_BYTES;
     double* scratch = scratch_all + wg * 12;
     const int flusher = blockIdx.x * NT + wg;
     const long long row_lo = (long long)flusher * P.rows_per_wg;
@@ -201,54 +228,34 @@ realnvp_small_tc_kernel(Params P, const void* __restrict__ xv, long long ld, con
       float ldj = 0.f, gmax = 0.f;
       for (int l = 0; l < nl; ++l, ++it) {
         const bool scaled = l < P.nscaled;
-        const float* S = s_scal + l * SF;
+        const float* tail = s_scal + l * SF;
+        // ---- GEMM1's A operand: [hs(y0) | 1 | lo(y0) | 0 | hs(y0) | 1 | 0] as 16 halves
+        {
+          uint16_t k16[16];
 #pragma unroll
-        for (int i = 0; i < d; ++i) gmax = fmaxf(gmax, fabsf(y[i]));  // fmaxf drops NaN: NaN rows do not trip the guard
-        // ---- relu(H) and its FP16 split, 16 hidden units per TMEM chunk
-#pragma unroll 1
-        for (int c = 0; c < HID / 16; ++c) {
-          if (c == 4 || c == 6) {  // quarters 2 / 3 reuse the buffers of quarters 0 / 1: their MMAs must have completed
-            mbar_wait(BAR(B_QD + NT * ((c >> 1) & 1) + wg), it & 1);
-            tc_fence_after();
+          for (int k = 0; k < 16; ++k) k16[k] = 0;
+          k16[K_ONE] = 0x3C00;
+          k16[K_ONE2] = 0x3C00;
+#pragma unroll
+          for (int i = 0; i < d; ++i) {
+            gmax = fmaxf(gmax, fabsf(y[i]));  // fmaxf drops NaN: NaN rows do not trip the guard
+            const uint16_t hs = to_f16(y[i]);
+            k16[K_HS + i] = hs;
+            k16[K_HS2 + i] = hs;
+            k16[K_LO + i] = to_f16(y[i] - from_f16(hs));
           }
-          const uint32_t ta = tm_a + 32 * ((c >> 1) & 1) + 16 * (c & 1);
-          uint32_t wl[8], wh[8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {  // four hidden units per group: their records are 4 (1 + d) contiguous floats
-            const float4* rec = reinterpret_cast<const float4*>(S + (16 * c + 4 * g) * RF);
-            float w[4 * RF];
-#pragma unroll
-            for (int i4 = 0; i4 < RF; ++i4) {
-              const float4 t4 = rec[i4];
-              w[4 * i4] = t4.x; w[4 * i4 + 1] = t4.y; w[4 * i4 + 2] = t4.z; w[4 * i4 + 3] = t4.w;
-            }
-            float h[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float acc = w[e * RF];
-#pragma unroll
-              for (int i = 0; i < d; ++i) acc = fmaf(y[i], w[e * RF + 1 + i], acc);
-              h[e] = acc;
-            }
-#pragma unroll
-            for (int pr = 0; pr < 2; ++pr) {
-              const uint32_t hs = pack_relu_rz_f16x2(h[2 * pr + 1], h[2 * pr]);
-              float l0, l1;
-              split_rest<false>(hs, h[2 * pr], h[2 * pr + 1], l0, l1);
-              wh[2 * g + pr] = hs;
-              wl[2 * g + pr] = pack_relu_f16x2(l1, l0);
-            }
-          }
-          tmem_st8(ta, wl);
-          tmem_st8(ta + 8, wh);
-          if (c & 1) {  // a K = 32 quarter is complete
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(BAR(B_AQ + NT * (c >> 1) + wg));
-          }
+          uint4 g0, g1;
+          g0.x = k16[0] | ((uint32_t)k16[1] << 16); g0.y = k16[2] | ((uint32_t)k16[3] << 16);
+          g0.z = k16[4] | ((uint32_t)k16[5] << 16); g0.w = k16[6] | ((uint32_t)k16[7] << 16);
+          g1.x = k16[8] | ((uint32_t)k16[9] << 16); g1.y = k16[10] | ((uint32_t)k16[11] << 16);
+          g1.z = k16[12] | ((uint32_t)k16[13] << 16); g1.w = k16[14] | ((uint32_t)k16[15] << 16);
+          *reinterpret_cast<uint4*>(a1 + tid * 16) = g0;
+          *reinterpret_cast<uint4*>(a1 + TILE * 16 + tid * 16) = g1;
         }
-        // ---- the linear part y0 V + v0 while the MMAs run
-        const float* tail = S + HID * RF;
+        fence_proxy_async();
+        tc_fence_before();  // orders the previous layer's TMEM loads (O) before the next MMAs
+        mbar_arrive(BAR(B_A1FULL + wg));
+        // ---- the linear part y0 V + v0 while GEMM1 runs
         float sh[u], sc[u];
 #pragma unroll
         for (int k = 0; k < u; ++k) {
@@ -261,18 +268,41 @@ realnvp_small_tc_kernel(Params P, const void* __restrict__ xv, long long ld, con
           sh[k] = t;
           sc[k] = s;
         }
+        // ---- E1: relu(H) -> (hs, lo) in place, the next chunk's load in flight under the current chunk's arithmetic
+        mbar_wait(BAR(B_HFULL + wg), it & 1);
+        tc_fence_after();
+        {
+          uint32_t va[16], vb[16];
+          tmem_ld16(tm_p, va);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t(&cur)[16] = (c & 1) ? vb : va;
+            uint32_t(&nxt)[16] = (c & 1) ? va : vb;
+            tmem_ld_wait16(cur);
+            if (c < 7) tmem_ld16(tm_p + (c + 1) * 16, nxt);
+            uint32_t wl[8], wh[8];
+            e1_chunk(cur, wl, wh);
+            tmem_st8(tm_p + c * 16, wl);
+            tmem_st8(tm_p + c * 16 + 8, wh);
+            if (c & 1) {  // a K = 32 quarter is complete
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(BAR(B_AQ + NT * (c >> 1) + wg));
+            }
+          }
+        }
+        // ---- E2
         mbar_wait(BAR(B_OFULL + wg), it & 1);
         tc_fence_after();
         uint32_t o[16];
         tmem_ld16(tm_o, o);
         tmem_ld_wait();
-        tc_fence_before();  // orders this load before the next layer's MMAs (issued after the next AFULL)
         float prod = 1.f;  // u <= 4 factors in [1e-3, 1e3] stay inside the float32 range
 #pragma unroll
         for (int k = 0; k < u; ++k) {
-          float y1 = y[d + k] - fmaf(__uint_as_float(o[k]), SU_INV, sh[k]);
+          float y1 = y[d + k] - fmaf(__uint_as_float(o[k]), SO_INV, sh[k]);
           if (scaled) {
-            const float a = fmaf(__uint_as_float(o[u + k]), SU_INV, sc[k]);
+            const float a = fmaf(__uint_as_float(o[u + k]), SO_INV, sc[k]);
             float s = softplus_clip_fast(a);
             s = (a != a) ? a : s;  // keep NaN (fminf / fmaxf would drop it)
             y1 *= rcp_approx(s);
@@ -339,10 +369,10 @@ int realnvp_small_tc_prepare(Flow* f) {
   if (ds.kind != HB_FLOW_REALNVP || D < 2 || D > 8) return HB_OK;
   const int d = f->d, u = f->u, nl = f->nlayers, ns = ds.n_scaled;
   if (d != stc::small_d(D) || nl < 1) return HB_OK;
-  const int RF = stc::rec_floats(D), SF = stc::scal_floats(D), UP = (u + 3) & ~3;
+  const int SF = stc::scal_floats(D), UP = (u + 3) & ~3;
   const size_t img_bytes = (size_t)nl * stc::L_BYTES;
-  const size_t smem = img_bytes + (((size_t)nl * SF * 4 + 15) & ~(size_t)15) + 8 * stc::B_COUNT + 16 +
-                      stc::NT * 12 * sizeof(double);
+  const size_t smem = img_bytes + (size_t)stc::NT * stc::A1_BYTES + (((size_t)nl * SF * 4 + 15) & ~(size_t)15) +
+                      8 * stc::B_COUNT + 16 + stc::NT * 12 * sizeof(double);
   if (smem > 200 * 1024) return HB_OK;
   const double slope = 0.01, c = 1.0 - slope;  // leaky_relu(h) = slope h + c relu(h)
   std::vector<uint8_t> img(img_bytes, 0);
@@ -358,19 +388,29 @@ int realnvp_small_tc_prepare(Flow* f) {
     const float* bt = Wt + (size_t)128 * u;
     const float* Ws = bt + u;
     const float* bs = Ws + (size_t)128 * u;
-    float* S = scal.data() + (size_t)l * SF;
+    uint8_t* lay = img.data() + (size_t)l * stc::L_BYTES;
+    // GEMM1 block [128 x 16 K'] times SH: hi rows meet hs and lo of the inputs, lo rows meet hs; the bias meets the ones
+    uint16_t* g16 = reinterpret_cast<uint16_t*>(lay);
     for (int j = 0; j < 128; ++j) {
-      float* rec = S + (size_t)j * RF;
-      rec[0] = b0[j];
       double sum = 0.0;
       for (int i = 0; i < d; ++i) {
-        rec[1 + i] = W0[(size_t)i * 128 + j];
+        float hi, lo;
+        split_hi_lo(W0[(size_t)i * 128 + j], &hi, &lo);
+        const uint16_t h16 = f32_to_f16(hi * stc::SH, &overflow), l16 = f32_to_f16(lo * stc::SH, &overflow);
+        g16[kmajor_off16(128, j, stc::K_HS + i)] = h16;
+        g16[kmajor_off16(128, j, stc::K_LO + i)] = h16;
+        g16[kmajor_off16(128, j, stc::K_HS2 + i)] = l16;
         sum += fabs((double)W0[(size_t)i * 128 + j]);
       }
+      float hi, lo;
+      split_hi_lo(b0[j], &hi, &lo);
+      g16[kmajor_off16(128, j, stc::K_ONE)] = f32_to_f16(hi * stc::SH, &overflow);
+      g16[kmajor_off16(128, j, stc::K_ONE2)] = f32_to_f16(lo * stc::SH, &overflow);
       if (sum > hsum_max) hsum_max = sum;
       if (fabs((double)b0[j]) > hbias_max) hbias_max = fabs((double)b0[j]);
     }
-    float* tl = S + (size_t)128 * RF;
+    // the linear part: row 0 = b2 + slope b0 W2, rows 1..d = slope W0 W2 (float64 sums, rounded once)
+    float* tl = scal.data() + (size_t)l * SF;
     for (int half = 0; half < (scaled ? 2 : 1); ++half) {
       const float* W2 = half ? Ws : Wt;
       const float* b2 = half ? bs : bt;
@@ -385,9 +425,9 @@ int realnvp_small_tc_prepare(Flow* f) {
         }
       }
     }
-    // B blocks: rows 0..u-1 = c Wt, rows u..2u-1 = c Ws (scaled layers), times SU, hi | lo
+    // GEMM2 blocks: rows 0..u-1 = c Wt, rows u..2u-1 = c Ws (scaled layers), times SU, hi | lo
     for (int q = 0; q < 4; ++q) {
-      uint16_t* c16 = reinterpret_cast<uint16_t*>(img.data() + (size_t)l * stc::L_BYTES + (size_t)q * stc::Q_BYTES);
+      uint16_t* c16 = reinterpret_cast<uint16_t*>(lay + stc::G1_BYTES + (size_t)q * stc::Q_BYTES);
       for (int kk = 0; kk < 32; ++kk) {
         const int j = 32 * q + kk;
         for (int n = 0; n < (scaled ? 2 * u : u); ++n) {
@@ -401,8 +441,17 @@ int realnvp_small_tc_prepare(Flow* f) {
     }
   }
   if (overflow) return HB_OK;
-  double limit = 1e30;
-  if (hsum_max > 0.0) limit = (60000.0 - hbias_max) / hsum_max;
+  // hs = fp16(SH relu(h)) and fp16(y0) must stay finite; and far outside the trained range the truncating accumulator
+  // of the K = 128 contraction shows against a float32 FMA chain: on the cfg3 flow with inputs 4 - 8 sigma wide every row
+  // that leaves max(1e-5, 3 x float32's own error) has a conditioning input beyond 128, none below (tools/
+  // stc_guard_calib.py, profiles/r2_stc_guard_calib.txt).  Rows beyond HALF of that are counted and AUTO evaluates the
+  // call on the CUDA cores (the ndim-64 kernel's policy)
+  double limit = 64.0;
+  if (const char* e = getenv("HB_STC_GUARD_LIMIT")) limit = atof(e);  // development aid (tools/stc_guard_calib.py)
+  if (hsum_max > 0.0) {
+    const double hl = (60000.0 / stc::SH - hbias_max) / hsum_max;
+    if (hl < limit) limit = hl;
+  }
   if (!(limit > 1.0)) return HB_OK;
   SmallTcCache* cch = new SmallTcCache();
   HB_CUDA(cudaMalloc(&cch->bimg, img.size()));
@@ -414,7 +463,7 @@ int realnvp_small_tc_prepare(Flow* f) {
     HB_CUDA(cudaMemset(f->tc_guard, 0, sizeof(unsigned long long)));
   }
   cch->smem = smem;
-  cch->guard_limit = (float)(limit < 1e30 ? limit : 1e30);
+  cch->guard_limit = (float)limit;
   f->stc = cch;
   f->tc_ok = true;
   return HB_OK;

@@ -597,3 +597,36 @@ def test_realnvp_small_tcgen05_fused_vs_oracle(dtype):
     ev3.add_chains(hm.Chains.from_arrays(view, lnp, start))
     host = hm.Chains.from_arrays(view.cpu().numpy(), lnp.cpu().numpy(), start)
     util.assert_evidence_close(ev3, util.oracle_evidence(m, host))
+
+
+_STC_THRESHOLD_SCRIPT = r"""
+import numpy as np
+from harmonic_b200 import _lib
+from tests import util
+m = util.make_realnvp(5, 6, 2, seed=3, standardize=True, ws=0.3)
+x = np.random.default_rng(2).standard_normal((4000, 5))
+x[11, 2] = 3.0e6   # would trip the tensor path's guard
+auto = m.predict(x)
+m2 = util.make_realnvp(5, 6, 2, seed=3, standardize=True, ws=0.3)
+m2.kernel_path = _lib.HB_PATH_SIMT
+assert np.array_equal(auto, m2.predict(x))
+import ctypes
+rows, calls = ctypes.c_int64(0), ctypes.c_int64(0)
+_lib.check(_lib.load().hb_flow_guard_stats(m._get_handle(0), ctypes.byref(rows), ctypes.byref(calls)))
+assert calls.value == 0
+print("threshold ok")
+"""
+
+
+def test_realnvp_small_tcgen05_default_row_threshold():
+    """Without HB_STC_MIN_ROWS (the test suite sets it to 0) a small AUTO call runs the register kernel: bit-identical to
+    HB_PATH_SIMT, no guard read, no guard trip."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k != "HB_STC_MIN_ROWS"}
+    out = subprocess.run([sys.executable, "-c", _STC_THRESHOLD_SCRIPT], cwd=root, env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and "threshold ok" in out.stdout, out.stdout + out.stderr
