@@ -117,8 +117,9 @@ size_t hb_flow_weight_count(const hb_flow_desc* desc);
 int hb_flow_create(const hb_flow_desc* desc, const float* weights, size_t n_weights, int device,
                    hb_flow** out);
 int hb_flow_destroy(hb_flow* flow);
-/* HB_PATH_*.  HB_PATH_TCGEN05 exists for RealNVP at ndim 64 (<= 8 coupling layers) and for RQSpline at ndim 2 (two
- * hidden layers, first one 32 or 64 wide, 8 bins); HB_PATH_AUTO takes it where it exists.  Returns
+/* HB_PATH_*.  HB_PATH_TCGEN05 exists for RealNVP at ndim 64 (<= 8 coupling layers) and at ndim 2..8, and for RQSpline
+ * at ndim 2 (two hidden layers, first one 32 or 64 wide, 8 bins); HB_PATH_AUTO takes it where it exists (RealNVP at
+ * ndim 2..8: from 2^20 rows per call on, below that the register kernel).  Returns
  * HB_ERR_UNSUPPORTED if the path cannot run this flow. */
 int hb_flow_set_path(hb_flow* flow, int path);
 /* 1 if the tcgen05 path will be used for this flow */
