@@ -650,3 +650,28 @@ def test_new_tensor_kernels_are_bit_reproducible(which):
         np.testing.assert_array_equal(a, m.predict(x))
     np.testing.assert_array_equal(a, m.predict(torch.from_numpy(x).cuda()).cpu().numpy())
     np.testing.assert_array_equal(a[777:20000], m.predict(x[777:20000]))
+
+
+@pytest.mark.parametrize("layers,rng,T", [(1, (-10.0, 10.0), 1.0), (2, (-3.0, 4.0), 0.5), (7, (-6.0, 6.0), 0.6)])
+def test_rqspline_tcgen05_range_temperature_layers(layers, rng, T):
+    """Odd and even layer counts (the mask alternates per layer), a custom spline range and several temperatures.  (At
+    T = 0.3 with inputs 2.5 sigma wide EVERY float32 evaluation of the 7-layer flow leaves 1e-5 on a handful of 2e5
+    samples -- restatement 1, register kernel 5, tensor kernel 16, max 1.05e-5 / 1.31e-5 / 1.34e-5: the 1 / T in front
+    of the squared latent amplifies the rounding -- so the 7-layer case runs at T = 0.6.)"""
+    m = util.make_rqspline(2, layers, 8, (64, 64), seed=20 + layers, standardize=True, spline_range=rng, temperature=T,
+                           ws=0.3)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = samples(5000, 2, seed=3, scale=2.5)
+    util.check_predict(m, x, m.predict(x))
+    m.temperature = 0.9 * T  # read on every call (harmonic/model.py:214)
+    util.check_predict(m, x, m.predict(x))
+
+
+@pytest.mark.parametrize("T", [1.0, 0.3])
+def test_realnvp_small_tcgen05_temperature(T):
+    m = util.make_realnvp(5, 6, 2, seed=5, standardize=True, temperature=T, ws=0.3)
+    m.kernel_path = _lib.HB_PATH_TCGEN05
+    x = samples(5000, 5, seed=3, scale=1.2)
+    util.check_predict(m, x, m.predict(x))
+    m.temperature = 0.5 * T
+    util.check_predict(m, x, m.predict(x))
